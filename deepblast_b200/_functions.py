@@ -1,0 +1,103 @@
+"""torch.autograd glue shared by deepblast_b200.nw_cuda and deepblast_b200.sw_cuda.
+
+Mirrors deepblast/nw_cuda.py:168-325 (and sw_cuda.py:168-326) name for name:
+same forward/backward signatures, same saved tensors, same returned tuples
+(grad wrt A is A itself, nw_cuda.py:206-207; double backward returns None for A,
+nw_cuda.py:262), same TypeError / NotImplementedError checks (nw_cuda.py:171-175).
+Not replicated on purpose: torch.autograd.set_detect_anomaly(True) at import
+(nw_cuda.py:9) and the A[last, j-1] indexing of the Numba kernels (nw_cuda.py:61);
+results follow deepblast/nw.py / sw.py.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def make_classes(mode, prefix):
+    class FunctionBackward(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, theta, A, Et, Q, operator):
+            if operator != 'softmax':
+                raise NotImplementedError(
+                    "CUDA variant only supports 'softmax' operator")
+            lens = getattr(Q, "_b200dp_lens", (None, None))
+            E = ops.backward_pass(Et, Q, mode, lens[0], lens[1])
+            ctx.save_for_backward(Q, E)
+            ctx.others = operator
+            ctx.lens = lens
+            return E, A
+
+        @staticmethod
+        def backward(ctx, Ztheta, ZA):
+            Q, E = ctx.saved_tensors
+            B, ZN, ZM = Ztheta.shape
+            if ZA is None:
+                ZA = torch.zeros((B, ZN - 2, ZM - 2), dtype=Ztheta.dtype, device=Ztheta.device)
+            xl, yl = ctx.lens
+            Vtd, Qd = ops.adjoint_forward_pass(Q, Ztheta, ZA, xl, yl)
+            Ed = ops.adjoint_backward_pass(E, Q, Qd, xl, yl)
+            Ed = Ed[:, 1:-1, 1:-1]
+            return Ed, None, Vtd, None, None, None
+
+    class Function(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, theta, A, operator, xlen=None, ylen=None):
+            if operator != 'softmax':
+                raise NotImplementedError(
+                    "CUDA variant only supports 'softmax' operator")
+            if theta.dtype != torch.float32:
+                raise TypeError("CUDA variant only supports torch.float32 type")
+            Vt, Q = ops.forward_pass(theta, A, mode, xlen, ylen)
+            if xlen is not None or ylen is not None:
+                Q._b200dp_lens = (xlen, ylen)
+            ctx.save_for_backward(theta, A, Q)
+            ctx.others = operator
+            ctx.lens = (xlen, ylen)
+            return Vt
+
+        @staticmethod
+        def backward(ctx, Et):
+            theta, A, Q = ctx.saved_tensors
+            operator = ctx.others
+            if ctx.lens != (None, None):
+                Q._b200dp_lens = ctx.lens
+            E, A = FunctionBackward.apply(theta, A, Et, Q, operator)
+            return E[:, 1:-1, 1:-1], A, None, None, None
+
+    class Decoder(nn.Module):
+        def __init__(self, operator):
+            super().__init__()
+            self.operator = operator
+
+        def forward(self, theta, A, xlen=None, ylen=None):
+            if xlen is None and ylen is None:
+                return Function.apply(theta, A, self.operator)
+            return Function.apply(theta, A, self.operator, xlen, ylen)
+
+        def traceback(self, grad):
+            """Greedy walk over one [N, M] expected-alignment matrix; the rule of
+            deepblast/nw_cuda.py:273-317, evaluated by one kernel launch."""
+            if not torch.is_tensor(grad):
+                grad = torch.as_tensor(grad)
+            if not grad.is_cuda:
+                grad = grad.cuda()
+            return ops.traceback_batch(grad.unsqueeze(0), variant="cuda")[0]
+
+        def traceback_batch(self, grad, xlen=None, ylen=None, variant="cuda"):
+            """All pairs of a [B, N, M] batch in one launch."""
+            return ops.traceback_batch(grad, xlen, ylen, variant)
+
+        def decode(self, theta, A, xlen=None, ylen=None):
+            """ Shortcut for doing inference. """
+            with torch.enable_grad():
+                nll = self.forward(theta, A, xlen, ylen)
+                v = torch.sum(nll)
+                v_grad, _ = torch.autograd.grad(v, (theta, A), create_graph=True)
+            return v_grad
+
+    for cls, suffix in ((FunctionBackward, "FunctionBackward"), (Function, "Function"),
+                        (Decoder, "Decoder")):
+        cls.__name__ = prefix + suffix
+        cls.__qualname__ = prefix + suffix
+    return Function, FunctionBackward, Decoder

@@ -1,0 +1,55 @@
+"""ctypes binding of libb200dp.so (include/b200dp.h).  Fails loudly when the
+library is missing: there is no CPU or PyTorch fallback on this path."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200dp.so")
+
+_lib = None
+
+_f = ctypes.c_void_p      # device pointers travel as integers
+_i = ctypes.c_int
+_ll = ctypes.c_longlong
+
+EXPORTS = {
+    "b200dp_version": (ctypes.c_int, []),
+    "b200dp_last_error": (ctypes.c_char_p, []),
+    "b200dp_q_layout": (ctypes.c_int, [_i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i),
+                                       ctypes.POINTER(_ll), ctypes.POINTER(_i)]),
+    "b200dp_fwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
+    "b200dp_bwd": (ctypes.c_int, [_f, _ll, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
+    "b200dp_adj_fwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f]),
+    "b200dp_adj_bwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f]),
+    "b200dp_traceback": (ctypes.c_int, [_f, _ll, _ll, _ll, _f, _f, _i, _i, _i, _i, _f, _i, _f, _f]),
+}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m deepblast_b200.build` "
+                "(nvcc, sm_100a).  deepblast_b200 has no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().b200dp_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def q_layout(N, M):
+    Lp, ND, off = _i(), _i(), _i()
+    ps = _ll()
+    check(lib().b200dp_q_layout(N, M, ctypes.byref(Lp), ctypes.byref(ND),
+                                ctypes.byref(ps), ctypes.byref(off)), "b200dp_q_layout")
+    return Lp.value, ND.value, ps.value, off.value

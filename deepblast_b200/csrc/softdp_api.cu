@@ -1,0 +1,364 @@
+// softdp_api.cu -- C ABI of libb200dp.so (declared in include/b200dp.h).
+// Host side: argument checks, TMA tensor-map encoding, launch geometry, launches.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/b200dp.h"
+#include "softdp_adjoint.cuh"
+#include "softdp_bwd.cuh"
+#include "softdp_fwd.cuh"
+#include "softdp_traceback.cuh"
+
+using namespace b200dp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct DevInfo {
+    int sms = 0;
+    int smem_optin = 0;
+    int smem_per_sm = 0;
+};
+
+bool dev_info(DevInfo& out) {
+    static DevInfo cache[64];
+    static bool have[64] = {false};
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!have[dev]) {
+        DevInfo d;
+        if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+        cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&d.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        cache[dev] = d;
+        have[dev] = true;
+    }
+    out = cache[dev];
+    return true;
+}
+
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// rank-3 map over a contiguous [B, N, M] fp32 tensor, box 32 cols x 32 rows x 1
+bool encode_row_map(CUtensorMap* map, const float* ptr, int B, int N, int M) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)M, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)M * 4, (cuuint64_t)N * M * 4};
+    cuuint32_t box[3] = {kTile, kTile, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// rank-4 map over anti-diagonal-major Q storage [B][ND][3][Lp], box 32 x 3 x kDiagRows x 1
+bool encode_q_map(CUtensorMap* map, const float* ptr, int B, const QLayout& ql) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)ql.Lp, 3, (cuuint64_t)ql.ND, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ql.Lp * 4, (cuuint64_t)ql.Lp * 12, (cuuint64_t)ql.pair_stride * 4};
+    cuuint32_t box[4] = {32, 3, kDiagRows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+QLayout q_layout(int N, int M) {
+    QLayout ql;
+    ql.Lp = ((N + 33 + 31) / 32) * 32;
+    ql.ND = N + M + 3;
+    ql.pair_stride = (long long)ql.ND * 3 * ql.Lp;
+    return ql;
+}
+
+int check_common(const char* fn, int B, int N, int M) {
+    if (B < 0 || N < 1 || M < 1) return fail(-1, std::string(fn) + ": need B >= 0, N >= 1, M >= 1");
+    if ((long long)N + M > (1 << 24)) return fail(-1, std::string(fn) + ": lattice too large");
+    return 0;
+}
+
+// Launch geometry.  A pair is cut into K = ceil(N/32) strips; W warps of one CTA work
+// on one pair at a time.  Pick W (a power of two) and the grid so that the estimated
+// sweep time  ceil(B / grid) * ceil(K / W) * (M + 33)  is smallest; ties go to the
+// smaller W (fewer cross-warp hand-offs).
+struct Geometry {
+    int W;
+    int grid;
+    size_t smem;
+};
+
+template <class SmemFn>
+int pick_geometry(const char* fn, int B, int N, int M, int flags, SmemFn smem_of, Geometry& g) {
+    DevInfo di;
+    if (!dev_info(di)) return fail(-2, std::string(fn) + ": cannot query the CUDA device");
+    const int K = (N + kTile - 1) / kTile;
+    int forceW = (flags >> B200DP_WARPS_SHIFT) & 0xF;
+    int forceG = (flags >> B200DP_CTAS_SHIFT) & 0xFFFF;
+    if (const char* e = getenv("B200DP_WARPS")) forceW = atoi(e);
+    if (const char* e = getenv("B200DP_CTAS")) forceG = atoi(e);
+    double best = 1e300;
+    g.W = 0;
+    for (int W = 1; W <= 8; W *= 2) {
+        if (forceW ? (W != forceW) : (W > 1 && W > K)) continue;
+        size_t smem = smem_of(W, M);
+        if (smem > (size_t)di.smem_optin) continue;
+        int per_sm = (int)((size_t)di.smem_per_sm / (smem + 1024));   // 1 KB reserved per CTA
+        per_sm = per_sm < 1 ? 1 : per_sm;
+        int by_threads = 2048 / (32 * W);
+        if (per_sm > by_threads) per_sm = by_threads;
+        if (per_sm > 32) per_sm = 32;
+        long long resident = (long long)di.sms * per_sm;
+        int grid = (int)(B < resident ? B : resident);
+        if (grid < 1) grid = 1;
+        double rounds = (double)((B + grid - 1) / grid);
+        double t = rounds * (double)((K + W - 1) / W) * (double)(M + 33);
+        if (t < best * 0.999) {
+            best = t;
+            g.W = W;
+            g.grid = grid;
+            g.smem = smem;
+        }
+    }
+    if (!g.W) return fail(-3, std::string(fn) + ": M too large for shared memory boundary rows");
+    if (forceG > 0) g.grid = forceG;
+    return 0;
+}
+
+template <class Kern>
+int set_smem(Kern k, size_t smem, const char* fn) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, fn);
+    return 0;
+}
+
+bool env_no_tma() {
+    const char* e = getenv("B200DP_NO_TMA");
+    return e && atoi(e) != 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200dp_version(void) { return 100; }
+
+const char* b200dp_last_error(void) { return g_err.c_str(); }
+
+int b200dp_q_layout(int N, int M, int* Lp, int* ND, long long* pair_stride, int* view_offset) {
+    if (N < 1 || M < 1) return fail(-1, "b200dp_q_layout: need N >= 1, M >= 1");
+    QLayout ql = q_layout(N, M);
+    if (Lp) *Lp = ql.Lp;
+    if (ND) *ND = ql.ND;
+    if (pair_stride) *pair_stride = ql.pair_stride;
+    if (view_offset) *view_offset = 31;
+    return 0;
+}
+
+int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const int32_t* xlen, const int32_t* ylen,
+               int B, int N, int M, int mode, int flags, void* stream) {
+    if (int rc = check_common("b200dp_fwd", B, N, M)) return rc;
+    if (mode != B200DP_MODE_NW && mode != B200DP_MODE_SW) return fail(-1, "b200dp_fwd: bad mode");
+    if (B == 0) return 0;
+    if (!theta || !A || !Q || !Vt) return fail(-1, "b200dp_fwd: null pointer");
+    if (!aligned(Q, 128)) return fail(-1, "b200dp_fwd: Q storage must be 128-byte aligned");
+    Geometry g;
+    if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd_smem_bytes, g)) return rc;
+    FwdParams p;
+    p.theta = theta;
+    p.A = A;
+    p.Q = Q;
+    p.Vt = Vt;
+    p.d = PairDims{xlen, ylen, B, N, M};
+    p.ql = q_layout(N, M);
+    p.i0 = mode == B200DP_MODE_SW ? 2 : 1;
+    p.flags = flags;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap tmT, tmA;
+    memset(&tmT, 0, sizeof(tmT));
+    memset(&tmA, 0, sizeof(tmA));
+    bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma() && (M % 4 == 0) && M >= kTile && N >= kTile &&
+               aligned(theta, 16) && aligned(A, 16);
+    if (tma) tma = encode_row_map(&tmT, theta, B, N, M) && encode_row_map(&tmA, A, B, N, M);
+    if (tma) {
+        if (int rc = set_smem(softdp_fwd_kernel<true>, g.smem, "b200dp_fwd")) return rc;
+        softdp_fwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(tmT, tmA, p);
+    } else {
+        if (int rc = set_smem(softdp_fwd_kernel<false>, g.smem, "b200dp_fwd")) return rc;
+        softdp_fwd_kernel<false><<<g.grid, 32 * g.W, g.smem, st>>>(tmT, tmA, p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "b200dp_fwd launch");
+    return 0;
+}
+
+int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E, const int32_t* xlen,
+               const int32_t* ylen, int B, int N, int M, int mode, int flags, void* stream) {
+    if (int rc = check_common("b200dp_bwd", B, N, M)) return rc;
+    if (mode != B200DP_MODE_NW && mode != B200DP_MODE_SW) return fail(-1, "b200dp_bwd: bad mode");
+    if (B == 0) return 0;
+    if (!Et || !Q || !E) return fail(-1, "b200dp_bwd: null pointer");
+    if (!aligned(Q, 128)) return fail(-1, "b200dp_bwd: Q storage must be 128-byte aligned");
+    Geometry g;
+    if (int rc = pick_geometry("b200dp_bwd", B, N, M, flags, bwd_smem_bytes, g)) return rc;
+    BwdParams p;
+    p.Et = Et;
+    p.et_stride = et_stride;
+    p.Q = Q;
+    p.E = E;
+    p.d = PairDims{xlen, ylen, B, N, M};
+    p.ql = q_layout(N, M);
+    p.i0 = mode == B200DP_MODE_SW ? 2 : 1;
+    p.flags = flags;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap tmQ;
+    memset(&tmQ, 0, sizeof(tmQ));
+    bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma();
+    if (tma) tma = encode_q_map(&tmQ, Q, B, p.ql);
+    if (tma) {
+        if (int rc = set_smem(softdp_bwd_kernel<true>, g.smem, "b200dp_bwd")) return rc;
+        softdp_bwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, p);
+    } else {
+        if (int rc = set_smem(softdp_bwd_kernel<false>, g.smem, "b200dp_bwd")) return rc;
+        softdp_bwd_kernel<false><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "b200dp_bwd launch");
+    return 0;
+}
+
+int b200dp_adj_fwd(const float* Q, const float* Ztheta, const float* ZA, float* Vtd, float* Qd,
+                   const int32_t* xlen, const int32_t* ylen, int B, int N, int M, int flags, void* stream) {
+    if (int rc = check_common("b200dp_adj_fwd", B, N, M)) return rc;
+    if (B == 0) return 0;
+    if (!Q || !Ztheta || !ZA || !Vtd || !Qd) return fail(-1, "b200dp_adj_fwd: null pointer");
+    if (!aligned(Q, 128) || !aligned(Qd, 128))
+        return fail(-1, "b200dp_adj_fwd: Q/Qd storage must be 128-byte aligned");
+    Geometry g;
+    if (int rc = pick_geometry("b200dp_adj_fwd", B, N, M, flags, adj_fwd_smem_bytes, g)) return rc;
+    AdjFwdParams p;
+    p.Q = Q;
+    p.Ztheta = Ztheta;
+    p.ZA = ZA;
+    p.Vtd = Vtd;
+    p.Qd = Qd;
+    p.d = PairDims{xlen, ylen, B, N, M};
+    p.ql = q_layout(N, M);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap tmQ;
+    memset(&tmQ, 0, sizeof(tmQ));
+    bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma();
+    if (tma) tma = encode_q_map(&tmQ, Q, B, p.ql);
+    if (tma) {
+        if (int rc = set_smem(softdp_adj_fwd_kernel<true>, g.smem, "b200dp_adj_fwd")) return rc;
+        softdp_adj_fwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, p);
+    } else {
+        if (int rc = set_smem(softdp_adj_fwd_kernel<false>, g.smem, "b200dp_adj_fwd")) return rc;
+        softdp_adj_fwd_kernel<false><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "b200dp_adj_fwd launch");
+    return 0;
+}
+
+int b200dp_adj_bwd(const float* E, const float* Q, const float* Qd, float* Ed, const int32_t* xlen,
+                   const int32_t* ylen, int B, int N, int M, int flags, void* stream) {
+    if (int rc = check_common("b200dp_adj_bwd", B, N, M)) return rc;
+    if (B == 0) return 0;
+    if (!E || !Q || !Qd || !Ed) return fail(-1, "b200dp_adj_bwd: null pointer");
+    if (!aligned(Q, 128) || !aligned(Qd, 128))
+        return fail(-1, "b200dp_adj_bwd: Q/Qd storage must be 128-byte aligned");
+    Geometry g;
+    if (int rc = pick_geometry("b200dp_adj_bwd", B, N, M, flags, adj_bwd_smem_bytes, g)) return rc;
+    AdjBwdParams p;
+    p.E = E;
+    p.Q = Q;
+    p.Qd = Qd;
+    p.Ed = Ed;
+    p.d = PairDims{xlen, ylen, B, N, M};
+    p.ql = q_layout(N, M);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap tmQ, tmQd;
+    memset(&tmQ, 0, sizeof(tmQ));
+    memset(&tmQd, 0, sizeof(tmQd));
+    bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma();
+    if (tma) tma = encode_q_map(&tmQ, Q, B, p.ql) && encode_q_map(&tmQd, Qd, B, p.ql);
+    if (tma) {
+        if (int rc = set_smem(softdp_adj_bwd_kernel<true>, g.smem, "b200dp_adj_bwd")) return rc;
+        softdp_adj_bwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, tmQd, p);
+    } else {
+        if (int rc = set_smem(softdp_adj_bwd_kernel<false>, g.smem, "b200dp_adj_bwd")) return rc;
+        softdp_adj_bwd_kernel<false><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, tmQd, p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "b200dp_adj_bwd launch");
+    return 0;
+}
+
+int b200dp_traceback(const float* grad, long long sb, long long si, long long sj, const int32_t* xlen,
+                     const int32_t* ylen, int B, int N, int M, int variant, int32_t* out, int cap, int32_t* len,
+                     void* stream) {
+    if (int rc = check_common("b200dp_traceback", B, N, M)) return rc;
+    if (variant != 0 && variant != 1) return fail(-1, "b200dp_traceback: bad variant");
+    if (B == 0) return 0;
+    if (!grad || !out || !len || cap < 1) return fail(-1, "b200dp_traceback: null pointer / cap < 1");
+    TracebackParams p;
+    p.grad = grad;
+    p.sb = sb;
+    p.si = si;
+    p.sj = sj;
+    p.xlen = xlen;
+    p.ylen = ylen;
+    p.B = B;
+    p.N = N;
+    p.M = M;
+    p.variant = variant;
+    p.out = out;
+    p.cap = cap;
+    p.len = len;
+    const int threads = 32;
+    softdp_traceback_kernel<<<(B + threads - 1) / threads, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "b200dp_traceback launch");
+    return 0;
+}
+
+}  // extern "C"

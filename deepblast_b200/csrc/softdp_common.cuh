@@ -1,0 +1,197 @@
+// softdp_common.cuh -- shared device helpers for the sm_100a soft-DP kernels.
+//
+// Data layout in HBM:
+//   theta, A, ZA : [B, N, M] fp32 row-major (reference layout, deepblast/nw.py:65-117)
+//   E, Ed, Ztheta: [B, N+2, M+2] fp32 row-major (reference layout, nw.py:347)
+//   Q, Qd        : logical [B, N+2, M+2, 3] (nw.py:105) stored ANTI-DIAGONAL-MAJOR:
+//                  elem(b,i,j,s) = b*pair_stride + (i+j)*3*Lp + s*Lp + (i+31),
+//                  Lp = roundup(N+33, 32).  A torch strided view with strides
+//                  (pair_stride, 3Lp+1, 3Lp, Lp) and storage offset 31 presents it
+//                  with the reference's logical shape.  One anti-diagonal of a
+//                  32-row strip is one 128-byte line per state, so the wavefront's
+//                  stores/loads are perfectly coalesced and TMA-tileable.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200dp {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kTile = 32;            // rows per strip == lanes; row-major tile is 32 x 32
+constexpr int kTileElems = kTile * kTile;
+constexpr int kRowRing = 3;          // theta/A (row-major, skewed read): 2 live tiles + 1 in flight
+constexpr int kDiagRows = 16;        // anti-diagonals per Q tile
+constexpr int kDiagElems = kDiagRows * 3 * 32;
+constexpr int kDiagRing = 4;         // Q tiles: 1 live + 3 in flight
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier ------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// ---- TMA (cp.async.bulk.tensor) -------------------------------------------
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// ---- cp.async (generic fallback when a tensor is not TMA-addressable) -------
+__device__ __forceinline__ void cp_async4_zfill(void* dst, const void* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(valid ? 4 : 0)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- cross-warp progress words (release/acquire at CTA scope) ------------------
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.cta.shared.u64 [%0], %1;" ::"r"(smem_u32(p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.cta.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+// ---- fast math -----------------------------------------------------------------
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- persistent strip iterator ---------------------------------------------------
+// A CTA owns pairs blockIdx.x, blockIdx.x + gridDim.x, ...; every pair is cut into
+// strips of 32 rows.  All strips of all the CTA's pairs form ONE linear sequence
+// q = 0, 1, 2, ...; warp w executes the strips with q % W == w in increasing q.
+// Strip q hands its boundary row to strip q+1 (when both belong to the same pair)
+// through shared memory slot q % (W+1).  Because strip q+W+1 is executed by the
+// same warp as strip q+1 and after it, a slot is never overwritten while read.
+struct Strip {
+    int pair;     // batch index
+    int k;        // strip ordinal inside the pair in PROCESSING order (0 = first processed)
+    int K;        // strips in the pair
+    int n, m;     // lattice of the pair
+    unsigned q;   // linear sequence number inside the CTA
+    bool valid;
+};
+
+struct PairDims {
+    const int* xlen;
+    const int* ylen;
+    int B, N, M;
+};
+
+__device__ __forceinline__ void strip_load_pair(Strip& s, const PairDims& d) {
+    s.n = d.xlen ? d.xlen[s.pair] : d.N;
+    s.m = d.ylen ? d.ylen[s.pair] : d.M;
+    s.K = (s.n > 0 && s.m > 0) ? ((s.n + kTile - 1) / kTile) : 0;
+}
+__device__ __forceinline__ void strip_seek(Strip& s, const PairDims& d, int w, int W) {
+    for (;;) {
+        if (s.pair >= d.B) {
+            s.valid = false;
+            return;
+        }
+        if (s.k >= s.K) {
+            s.pair += gridDim.x;
+            s.k = 0;
+            if (s.pair < d.B) strip_load_pair(s, d);
+            continue;
+        }
+        if ((int)(s.q & (unsigned)(W - 1)) == w) {
+            s.valid = true;
+            return;
+        }
+        s.k++;
+        s.q++;
+    }
+}
+__device__ __forceinline__ void strip_first(Strip& s, const PairDims& d, int w, int W) {
+    s.pair = blockIdx.x;
+    s.k = 0;
+    s.q = 0;
+    s.K = 0;
+    s.n = s.m = 0;
+    s.valid = false;
+    if (s.pair < d.B) strip_load_pair(s, d);
+    strip_seek(s, d, w, W);
+}
+__device__ __forceinline__ void strip_next(Strip& s, const PairDims& d, int w, int W) {
+    s.k++;
+    s.q++;
+    strip_seek(s, d, w, W);
+}
+
+// wait until boundary `q` has published at least `need` entries
+__device__ __forceinline__ int progress_wait(const unsigned long long* word, unsigned q, int need) {
+    for (;;) {
+        unsigned long long v = ld_acquire_u64(word);
+        if ((unsigned)(v >> 32) == q && (int)(unsigned)v >= need) return (int)(unsigned)v;
+        __nanosleep(32);
+    }
+}
+
+struct QLayout {
+    long long pair_stride;   // floats
+    int Lp;                  // floats per (diagonal, state) row, multiple of 32
+    int ND;                  // anti-diagonals per pair = N + M + 3
+};
+
+}  // namespace b200dp

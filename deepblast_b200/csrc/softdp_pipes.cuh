@@ -1,0 +1,96 @@
+// softdp_pipes.cuh -- per-warp shared-memory tile pipelines fed by TMA.
+//
+// Every warp owns its rings and its mbarriers; nothing here synchronises the CTA.
+// A pipe streams the tiles of the warp's strips in ONE linear order that runs
+// across strip and pair boundaries, so the prefetch never drains between strips.
+#pragma once
+#include "softdp_common.cuh"
+
+namespace b200dp {
+
+// Bookkeeping of one ring of R slots.  AHEAD = how far past the tile being waited
+// on the producer may run: R-1 for tiles that die when the next one starts,
+// R-2 for the skewed row-major tiles (tile a-1 is still read while tile a is live).
+template <int R, int AHEAD>
+struct TilePipe {
+    int issued;        // tiles issued so far, counted from tile 0 of the CURRENT strip
+    unsigned islot;    // slot the next issue goes to
+    unsigned wslot;    // slot the next wait looks at
+    unsigned phases;   // one parity bit per slot
+
+    __device__ __forceinline__ void reset() {
+        issued = 0;
+        islot = wslot = 0;
+        phases = 0;
+    }
+    // Issue everything the ring can hold when the warp is about to consume tile `a`
+    // of the current strip (Tcur tiles); tiles past the strip's end come from the
+    // warp's next strip (Tnxt tiles, if nvalid).  fn(from_next, tile_index, slot).
+    template <class IssueFn>
+    __device__ __forceinline__ void pump(int a, int Tcur, bool nvalid, int Tnxt, IssueFn&& fn) {
+        while (issued <= a + AHEAD) {
+            if (issued < Tcur) fn(false, issued, islot);
+            else if (nvalid && issued - Tcur < Tnxt) fn(true, issued - Tcur, islot);
+            else break;
+            issued++;
+            islot = (islot + 1 == R) ? 0u : islot + 1;
+        }
+    }
+    // Wait for the next tile in linear order; returns its slot.
+    __device__ __forceinline__ unsigned wait(uint64_t* bars) {
+        mbar_wait(&bars[wslot], (phases >> wslot) & 1u);
+        phases ^= 1u << wslot;
+        unsigned s = wslot;
+        wslot = (wslot + 1 == R) ? 0u : wslot + 1;
+        return s;
+    }
+    __device__ __forceinline__ void next_strip(int Tcur) { issued -= Tcur; }
+};
+
+// ---- row-major 32x32 tile (theta, A, ZA, Ztheta, E) ---------------------------
+// Logical element (r, c) of a pair (0-based lattice row/col) lives at
+// base + r*pitch + c.  Tile (rb, cb) covers rows 32rb.., cols 32cb..; it lands in
+// shared memory dense [32][32] so lane t reading (row t, col c) hits bank c%32:
+// the wavefront's skewed read (c = s - t) is conflict-free.
+struct RowSrc {
+    const float* base;   // element (0,0) of pair 0
+    long long pair_stride;
+    int pitch;
+    int rows, cols;      // addressable extent per pair (reads beyond are zero-filled)
+};
+
+// Generic path: 32 lanes x 32 cp.async (4 B) + one noinc arrive per lane.
+__device__ __forceinline__ void row_tile_load_generic(float* dst, uint64_t* bar, const RowSrc& src, int pair, int rb,
+                                                      int cb, int lane) {
+    const float* pb = src.base + (long long)pair * src.pair_stride;
+    const int col = cb * kTile + lane;
+    const bool cok = col >= 0 && col < src.cols;
+#pragma unroll 8
+    for (int r = 0; r < kTile; ++r) {
+        const int row = rb * kTile + r;
+        const bool ok = cok && row < src.rows;
+        const float* g = ok ? (pb + (long long)row * src.pitch + col) : src.base;
+        cp_async4_zfill(dst + r * kTile + lane, g, ok);
+    }
+    cp_async_mbar_arrive_noinc(bar);
+}
+
+// ---- anti-diagonal-major Q tile: [kDiagRows diagonals][3 states][32 rows] -------
+// Generic path for the same box the TMA map describes.
+__device__ __forceinline__ void diag_tile_load_generic(float* dst, uint64_t* bar, const float* q, const QLayout& ql,
+                                                       int pair, int ip0, int dlo, int lane) {
+    const float* pb = q + (long long)pair * ql.pair_stride;
+#pragma unroll 4
+    for (int dd = 0; dd < kDiagRows; ++dd) {
+        const int d = dlo + dd;
+        const bool ok = d >= 0 && d < ql.ND && (ip0 + lane) < ql.Lp;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            const float* g = ok ? (pb + ((long long)d * 3 + s) * ql.Lp + ip0 + lane) : q;
+            cp_async4_zfill(dst + (dd * 3 + s) * 32 + lane, g, ok);
+        }
+    }
+    cp_async_mbar_arrive_noinc(bar);
+}
+
+}  // namespace b200dp

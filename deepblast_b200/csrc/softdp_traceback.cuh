@@ -1,0 +1,94 @@
+// softdp_traceback.cuh -- batched greedy traceback over an expected-alignment
+// matrix (reference: deepblast/nw.py:401-444 "cpu" rule, deepblast/nw_cuda.py:273-317
+// "cuda" rule).  One thread per pair walks at most n+m steps; the reference does the
+// same walk in Python with three device->host syncs per step.
+#pragma once
+#include "softdp_common.cuh"
+
+namespace b200dp {
+
+struct TracebackParams {
+    const float* grad;          // [B, N, M] with element strides (sb, si, sj)
+    long long sb, si, sj;
+    const int* xlen;
+    const int* ylen;
+    int B, N, M;
+    int variant;                // 0: nw.py rule, 1: nw_cuda.py rule
+    int32_t* out;               // [B, cap, 3] triples (i, j, state), final (reversed) order
+    int cap;
+    int32_t* len;               // [B]; -1 capacity exceeded, -2 reference would raise IndexError
+};
+
+__device__ __forceinline__ int tb_wrap(int idx, int n) { return idx < 0 ? idx + n : idx; }
+
+__global__ void softdp_traceback_kernel(TracebackParams p) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const int n = p.xlen ? p.xlen[b] : p.N;
+    const int m = p.ylen ? p.ylen[b] : p.M;
+    const float* g = p.grad + (long long)b * p.sb;
+    int32_t* out = p.out + (long long)b * p.cap * 3;
+    // sentinels of nw.py:418 / nw_cuda.py:291, compared after rounding to fp32
+    const float sentinel = p.variant == 0 ? -100000.0f : -1e10f;
+    int i = n - 1, j = m - 1, len = 0, status = 0;
+    if (p.cap < 1 || n < 1 || m < 1) {
+        p.len[b] = -1;
+        return;
+    }
+    out[0] = i;
+    out[1] = j;
+    out[2] = 1;
+    len = 1;
+    for (;;) {
+        float left, diag, upper;
+        left = (i <= 0) ? sentinel : g[(long long)(i - 1) * p.si + (long long)j * p.sj];
+        if (i <= 0 && j <= 0) diag = sentinel;
+        else {
+            // Python negative indices wrap around (exactly one of i, j can be <= 0 here)
+            if (i - 1 < -n || j - 1 < -m) { status = -2; break; }
+            diag = g[(long long)tb_wrap(i - 1, n) * p.si + (long long)tb_wrap(j - 1, m) * p.sj];
+        }
+        if (j <= 0) upper = sentinel;
+        else {
+            if (i < -n) { status = -2; break; }
+            upper = g[(long long)tb_wrap(i, n) * p.si + (long long)(j - 1) * p.sj];
+        }
+        const bool stop = p.variant == 0
+                              ? (diag == sentinel && upper == sentinel && left == sentinel)
+                              : (diag == sentinel || upper == sentinel || left == sentinel);
+        if (stop) break;
+        int ij = 0;                      // torch.argmax: first maximal index
+        float best = left;
+        if (diag > best) { best = diag; ij = 1; }
+        if (upper > best) { best = upper; ij = 2; }
+        if (ij == 0) i -= 1;
+        else if (ij == 1) { i -= 1; j -= 1; }
+        else j -= 1;
+        if (len >= p.cap) { status = -1; break; }
+        out[3 * len] = i; out[3 * len + 1] = j; out[3 * len + 2] = ij; len++;
+    }
+    while (status == 0 && i > 0) {       // "take care of any outstanding gaps"
+        i--;
+        if (len >= p.cap) { status = -1; break; }
+        out[3 * len] = i; out[3 * len + 1] = j; out[3 * len + 2] = 0; len++;
+    }
+    while (status == 0 && j > 0) {
+        j--;
+        if (len >= p.cap) { status = -1; break; }
+        out[3 * len] = i; out[3 * len + 1] = j; out[3 * len + 2] = 2; len++;
+    }
+    if (status != 0) {
+        p.len[b] = status;
+        return;
+    }
+    for (int a = 0, z = len - 1; a < z; ++a, --z) {      // states[::-1]
+        for (int c = 0; c < 3; ++c) {
+            const int32_t tmp = out[3 * a + c];
+            out[3 * a + c] = out[3 * z + c];
+            out[3 * z + c] = tmp;
+        }
+    }
+    p.len[b] = len;
+}
+
+}  // namespace b200dp

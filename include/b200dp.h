@@ -1,0 +1,98 @@
+/*
+ * b200dp.h -- C ABI of libb200dp.so: the B200 (sm_100a) soft-DP alignment engine.
+ *
+ * One export per Numba-CUDA kernel of the reference (deepblast/nw_cuda.py,
+ * deepblast/sw_cuda.py @ ec661fa); a reference maintainer binds these with ctypes
+ * from the torch.autograd.Functions.  Plain pointers and
+ * sizes only; all device memory is owned by the caller (torch's allocator); the
+ * library never allocates, frees or retains device memory and never synchronises.
+ * Every launch goes to the CUDA stream passed in (cudaStream_t as void*).
+ *
+ * Return value: 0 on success, negative for argument errors, positive
+ * cudaError_t otherwise; b200dp_last_error() returns a thread-local message.
+ *
+ * Tensors (all float32, device pointers):
+ *   theta, A, ZA   [B, N, M]        contiguous row-major
+ *   E, Ed, Ztheta  [B, N+2, M+2]    contiguous row-major (padded lattice, nw.py:347)
+ *   Vt, Vtd        [B]
+ *   Q, Qd          logical [B, N+2, M+2, 3] (nw.py:105), stored anti-diagonal-major:
+ *                  element (b,i,j,s) at  b*pair_stride + (i+j)*3*Lp + s*Lp + i + 31
+ *                  with Lp, pair_stride from b200dp_q_layout(); the pointer passed
+ *                  is the STORAGE base (128-byte aligned).  State order x=0, m=1,
+ *                  y=2 (deepblast/constants.py:1).
+ *   xlen, ylen     optional int32[B] per-pair lattice sizes (1 <= n <= N,
+ *                  1 <= m <= M); NULL = every pair is N x M.  With lengths, each
+ *                  pair is computed exactly as the reference computes the slice
+ *                  theta[b, :n, :m] on its own (deepblast/alignment.py:165-169);
+ *                  E/Ed must then be zero-filled by the caller beforehand.
+ *
+ * mode: 0 = Needleman-Wunsch (nw.py), 1 = "Smith-Waterman" (sw.py: loops from 2).
+ */
+#ifndef B200DP_H
+#define B200DP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DP_MODE_NW 0
+#define B200DP_MODE_SW 1
+
+/* flags */
+#define B200DP_Q_ROW_BORDERS 0x1   /* fwd: also write Q[0,:,:], Q[n+1,:,:] (zeros, corner = 1) */
+#define B200DP_NO_TMA        0x2   /* stage tiles with cp.async instead of TMA (debug / unaligned) */
+#define B200DP_WARPS_SHIFT   4     /* bits 4..7: warps per pair (1,2,4,8); 0 = choose automatically */
+#define B200DP_CTAS_SHIFT    8     /* bits 8..23: grid size override; 0 = choose automatically */
+
+#define B200DP_TRACEBACK_CPU_RULE  0   /* deepblast/nw.py:401-444 */
+#define B200DP_TRACEBACK_CUDA_RULE 1   /* deepblast/nw_cuda.py:273-317 */
+
+int b200dp_version(void);
+const char* b200dp_last_error(void);
+
+/* Anti-diagonal-major Q/Qd geometry for an N x M lattice.
+ * view_offset (= 31) is the storage offset of logical element (0,0,0,0); the logical
+ * strides are (pair_stride, 3*Lp + 1, 3*Lp, Lp). */
+int b200dp_q_layout(int N, int M, int* Lp, int* ND, long long* pair_stride, int* view_offset);
+
+/* replaces _forward_pass_kernel, deepblast/nw_cuda.py:46-79 (sw_cuda.py:46-79):
+ * theta, A -> Vt, Q.  Q's column borders j = 0, j = m+1 are written (zeros); its
+ * row borders only with B200DP_Q_ROW_BORDERS (no pass reads them). */
+int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt,
+               const int32_t* xlen, const int32_t* ylen, int B, int N, int M,
+               int mode, int flags, void* stream);
+
+/* replaces _backward_pass_kernel, deepblast/nw_cuda.py:82-102 (sw_cuda.py:82-102):
+ * Et (element stride et_stride, 0 for an expanded scalar), Q -> E, borders included
+ * (zeros, E[N+1, M+1] = Et). */
+int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E,
+               const int32_t* xlen, const int32_t* ylen, int B, int N, int M,
+               int mode, int flags, void* stream);
+
+/* replaces _adjoint_forward_pass_kernel, deepblast/nw_cuda.py:105-139:
+ * Q, Ztheta (padded), ZA -> Vtd, Qd (interior cells). */
+int b200dp_adj_fwd(const float* Q, const float* Ztheta, const float* ZA, float* Vtd,
+                   float* Qd, const int32_t* xlen, const int32_t* ylen, int B, int N,
+                   int M, int flags, void* stream);
+
+/* replaces _adjoint_backward_pass_kernel, deepblast/nw_cuda.py:142-165:
+ * E, Q, Qd -> Ed (padded, zero borders). */
+int b200dp_adj_bwd(const float* E, const float* Q, const float* Qd, float* Ed,
+                   const int32_t* xlen, const int32_t* ylen, int B, int N, int M,
+                   int flags, void* stream);
+
+/* replaces the Python walk NeedlemanWunschDecoder.traceback,
+ * deepblast/nw.py:401-444 (variant 0) / deepblast/nw_cuda.py:273-317 (variant 1),
+ * batched: grad [B, N, M] with element strides (sb, si, sj) -> out [B, cap, 3]
+ * int32 triples (i, j, state) in the reference's returned order, len [B]
+ * (-1: cap too small, -2: the reference would raise IndexError). */
+int b200dp_traceback(const float* grad, long long sb, long long si, long long sj,
+                     const int32_t* xlen, const int32_t* ylen, int B, int N, int M,
+                     int variant, int32_t* out, int cap, int32_t* len, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DP_H */

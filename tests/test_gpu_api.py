@@ -1,0 +1,163 @@
+"""GPU tests of the drop-in autograd surface (deepblast_b200.nw_cuda / sw_cuda),
+modelled on the reference's own GPU tests (deepblast/tests/test_nw_cuda.py:25-87,
+test_sw_cuda.py) plus direct comparison with reference-generated goldens."""
+import numpy as np
+import pytest
+import torch
+from torch.autograd import gradcheck
+from torch.autograd.gradcheck import gradgradcheck
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["t_nw_cuda_5x5", "r8x8", "r17x23", "r33x40", "r64x48"]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def decoders():
+    from deepblast_b200.nw_cuda import NeedlemanWunschDecoder
+    from deepblast_b200.sw_cuda import SmithWatermanDecoder
+    return {"nw": NeedlemanWunschDecoder, "sw": SmithWatermanDecoder}
+
+
+def setup_small():
+    torch.manual_seed(2)
+    B, N, M = 3, 5, 5
+    theta = torch.rand(B, N, M, requires_grad=True, dtype=torch.float32, device=dev())
+    A = -1. * torch.ones_like(theta)
+    return theta, A
+
+
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+def test_gradcheck_like_reference(mode):
+    # test_nw_cuda.py:51-55, test_sw_cuda.py:50-55
+    needle = decoders()[mode]('softmax')
+    theta, A = setup_small()
+    gradcheck(needle, (theta, A), eps=1e-1, atol=1e-1, rtol=1e-1)
+
+
+def test_gradgradcheck_like_reference():
+    # test_nw_cuda.py:57-61
+    needle = decoders()["nw"]('softmax')
+    theta, A = setup_small()
+    gradgradcheck(needle, (theta, A), eps=1e-1, atol=1e-1, rtol=1e-1)
+
+
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+def test_decoding_known_answer(golden, golden_meta, mode):
+    # test_nw_cuda.py:64-76 / test_sw_cuda.py:58-70
+    theta = torch.tensor(golden["ref_make_data/theta"].astype(np.float32), device=dev())
+    theta.requires_grad_()
+    A = 0.1 * torch.ones_like(theta)
+    needle = decoders()[mode]('softmax')
+    v = needle(theta, A)
+    v.backward()
+    np.testing.assert_allclose(v.detach().cpu().numpy(), golden[f"ref_make_data/{mode}/Vt_f32"], rtol=1e-6)
+    np.testing.assert_allclose(theta.grad.cpu().numpy(), golden[f"ref_make_data/{mode}/grad_f32"], atol=1e-5)
+    decoded = needle.traceback(theta.grad.squeeze())
+    want_xy = golden_meta["known_answers"]["nw_cuda_xy" if mode == "nw" else "sw_cuda_xy"]
+    assert [list(x[:2]) for x in decoded] == want_xy
+    assert decoded == [tuple(r) for r in golden[f"ref_make_data/{mode}/tb_cuda_f32"].tolist()]
+    assert all(isinstance(v, int) for tup in decoded for v in tup)
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+def test_autograd_matches_reference(golden, name, mode):
+    """decode + double backward through our Functions == the reference's (nw.py:315-386)."""
+    g = lambda k: golden[f"{name}/{k}"]
+    theta = torch.tensor(g("theta"), device=dev(), requires_grad=True)
+    A = torch.tensor(g("A"), device=dev(), requires_grad=True)
+    W = torch.tensor(g("W"), device=dev())
+    dec = decoders()[mode]('softmax')
+    aln = dec.decode(theta, A)
+    assert aln.shape == theta.shape and aln.requires_grad
+    np.testing.assert_allclose(aln.detach().cpu().numpy(), g(f"{mode}/ag_aln"), atol=2e-5)
+    (aln * W).sum().backward()
+    scale = max(1.0, float(np.abs(g(f"{mode}/ag_theta_grad2")).max()))
+    np.testing.assert_allclose(theta.grad.cpu().numpy(), g(f"{mode}/ag_theta_grad2"), atol=1e-4 * scale)
+    assert A.grad is None and bool(g(f"{mode}/ag_A_grad_is_none"))      # nw_cuda.py:262
+    v = dec(theta, A)
+    g_theta, g_A = torch.autograd.grad(v.sum(), (theta, A))
+    np.testing.assert_allclose(g_theta.cpu().numpy(), g(f"{mode}/ag_g_theta"), atol=2e-5)
+    np.testing.assert_array_equal(g_A.cpu().numpy(), g(f"{mode}/ag_g_A"))   # grad wrt A is A (nw_cuda.py:206-207)
+
+
+def test_api_quirks():
+    from deepblast_b200.nw_cuda import NeedlemanWunschDecoder, NeedlemanWunschFunction
+    theta, A = setup_small()
+    dec = NeedlemanWunschDecoder('softmax')
+    with pytest.raises(NotImplementedError):
+        NeedlemanWunschFunction.apply(theta, A, 'sparsemax')
+    with pytest.raises(TypeError):
+        NeedlemanWunschFunction.apply(theta.double(), A.double(), 'softmax')
+    with pytest.raises(RuntimeError):           # decode needs both to require grad (nw.py:455-457)
+        dec.decode(theta, A)
+    A = A.clone().requires_grad_()
+    full = dec.decode(theta, A)
+    # non-contiguous slices as NeuralAligner.traceback passes them (alignment.py:166-169)
+    th3, A3 = theta[1, :4, :3].unsqueeze(0), A[1, :4, :3].unsqueeze(0)
+    assert not th3.is_contiguous()
+    sub = dec.decode(th3, A3)
+    ref = dec.decode(th3.contiguous().detach().requires_grad_(), A3.contiguous().detach().requires_grad_())
+    assert torch.equal(sub, ref)
+    assert full.device == theta.device and full.dtype == torch.float32
+    assert not torch.is_anomaly_enabled()       # nw_cuda.py:9 is deliberately not replicated
+
+
+def test_no_cpu_fallback():
+    from deepblast_b200.nw_cuda import NeedlemanWunschFunction
+    theta = torch.rand(1, 4, 4)
+    with pytest.raises(RuntimeError):
+        NeedlemanWunschFunction.apply(theta, -torch.ones_like(theta), 'softmax')
+
+
+def test_varlen_decoder_matches_per_pair():
+    from deepblast_b200.nw_cuda import NeedlemanWunschDecoder
+    g = torch.Generator().manual_seed(0)
+    B, N, M = 5, 48, 70
+    theta = torch.rand(B, N, M, generator=g).to(dev()).requires_grad_()
+    A = (-torch.rand(B, N, M, generator=g)).to(dev()).requires_grad_()
+    xlen = torch.tensor([48, 20, 33, 1, 47], dtype=torch.int32, device=dev())
+    ylen = torch.tensor([70, 64, 5, 9, 31], dtype=torch.int32, device=dev())
+    dec = NeedlemanWunschDecoder('softmax')
+    aln = dec.decode(theta, A, xlen, ylen)
+    Wt = torch.randn(B, N, M, generator=g).to(dev())
+    (aln * Wt).sum().backward()
+    g_all = theta.grad.clone()
+    for b in range(B):
+        n, m = int(xlen[b]), int(ylen[b])
+        th = theta[b:b + 1, :n, :m].detach().contiguous().requires_grad_()
+        a = A[b:b + 1, :n, :m].detach().contiguous().requires_grad_()
+        one = dec.decode(th, a)
+        assert torch.allclose(aln[b, :n, :m], one[0], atol=1e-6)
+        assert float(aln[b, n:, :].abs().sum()) == 0.0 and float(aln[b, :, m:].abs().sum()) == 0.0
+        (one * Wt[b:b + 1, :n, :m]).sum().backward()
+        assert torch.allclose(g_all[b, :n, :m], th.grad[0], atol=1e-4, rtol=1e-4)
+        assert float(g_all[b, n:, :].abs().sum()) == 0.0
+
+
+def test_install_patches_reference_names():
+    import sys
+    import types
+    import deepblast_b200
+    # a stand-in for an installed reference package (the real one is absent on the GPU box)
+    pkg = types.ModuleType("deepblast")
+    pkg.__path__ = []
+    for name in ("nw_cuda", "sw_cuda", "alignment"):
+        mod = types.ModuleType(f"deepblast.{name}")
+        sys.modules[f"deepblast.{name}"] = mod
+        setattr(pkg, name, mod)
+    sys.modules["deepblast"] = pkg
+    try:
+        patched = deepblast_b200.install()
+        from deepblast_b200.nw_cuda import NeedlemanWunschDecoder
+        from deepblast_b200.sw_cuda import SmithWatermanDecoder
+        assert sys.modules["deepblast.nw_cuda"].NeedlemanWunschDecoder is NeedlemanWunschDecoder
+        assert sys.modules["deepblast.alignment"].SWDecoderCUDA is SmithWatermanDecoder
+        assert "deepblast.nw_cuda.NeedlemanWunschFunction" in patched
+    finally:
+        for name in ("deepblast", "deepblast.nw_cuda", "deepblast.sw_cuda", "deepblast.alignment"):
+            sys.modules.pop(name, None)

@@ -1,0 +1,135 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol the header
+declares, host logic (layout, sharding), loud failure without a GPU, and a
+world_size-2 gloo run of the sharding logic."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_header_symbols():
+    from deepblast_b200 import _lib
+    from deepblast_b200.build import build
+    build()
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "b200dp.h")).read()
+    declared = set(re.findall(r"\b(b200dp_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name)
+    assert L.b200dp_version() >= 100
+
+
+def test_q_layout_is_a_valid_strided_view():
+    from deepblast_b200 import _lib
+    for N, M in [(1, 1), (5, 4), (31, 33), (32, 32), (256, 256), (300, 77), (1000, 2047)]:
+        Lp, ND, ps, off = _lib.q_layout(N, M)
+        assert Lp % 32 == 0 and Lp >= N + 33 and ND == N + M + 3 and ps == ND * 3 * Lp and off == 31
+        # the logical strides address distinct elements inside the pair's storage
+        i, j, s = np.meshgrid(np.arange(N + 2), np.arange(M + 2), np.arange(3), indexing="ij")
+        addr = off + i * (3 * Lp + 1) + j * (3 * Lp) + s * Lp
+        assert addr.min() >= 0 and addr.max() < ps
+        if (N + 2) * (M + 2) <= 40000:
+            assert len(np.unique(addr)) == addr.size
+        # interior rows of strip k start a 128-byte line: (i + 31) % 32 == 0 for i = 32k + 1
+        assert (1 + 31) % 32 == 0
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    from deepblast_b200 import _lib
+    L = _lib.lib()
+    assert L.b200dp_q_layout(0, 5, None, None, None, None) < 0
+    assert b"N >= 1" in L.b200dp_last_error()
+    assert L.b200dp_fwd(0, 0, 0, 0, 0, 0, 1, 0, 4, 0, 0, 0) < 0
+    assert L.b200dp_fwd(0, 0, 0, 0, 0, 0, 1, 4, 4, 7, 0, 0) < 0      # bad mode
+    assert L.b200dp_traceback(0, 0, 0, 0, 0, 0, 1, 4, 4, 5, 0, 1, 0, 0) < 0
+
+
+def test_cpu_tensors_fail_loudly():
+    from deepblast_b200.nw_cuda import NeedlemanWunschDecoder, NeedlemanWunschFunction
+    theta = torch.rand(1, 4, 4, requires_grad=True)
+    A = -torch.ones(1, 4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        NeedlemanWunschFunction.apply(theta, A, 'softmax')
+    with pytest.raises(NotImplementedError):
+        NeedlemanWunschFunction.apply(theta, A, 'hardmax')
+    with pytest.raises(TypeError):
+        NeedlemanWunschFunction.apply(theta.double(), A.double(), 'softmax')
+    assert NeedlemanWunschDecoder('softmax').operator == 'softmax'
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "deepblast_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle accumulates", ""), f
+
+
+def test_sharding_helpers():
+    from deepblast_b200.sharding import lpt_assign, packing_stats, shard_range
+    for B, W in [(8192, 8), (1024, 3), (5, 8), (0, 2)]:
+        ranges = [shard_range(B, W, r) for r in range(W)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == B
+        assert all(ranges[r][1] == ranges[r + 1][0] for r in range(W - 1))
+        sizes = [hi - lo for lo, hi in ranges]
+        assert max(sizes) - min(sizes) <= 1
+    rng = np.random.default_rng(0)
+    k = rng.choice(np.arange(1, 17), size=8192, p=(1 / np.arange(1, 17)) / (1 / np.arange(1, 17)).sum())
+    k2 = rng.choice(np.arange(1, 17), size=8192, p=(1 / np.arange(1, 17)) / (1 / np.arange(1, 17)).sum())
+    xlen, ylen = 64 * k, 64 * k2
+    asg = lpt_assign(xlen * ylen, 8)
+    assert sorted(np.concatenate(asg).tolist()) == list(range(8192))
+    st = packing_stats(xlen, ylen, asg)
+    assert st["imbalance"] < 1.01 and st["packing_efficiency"] == 1.0
+    for a in asg:
+        c = (xlen * ylen)[a]
+        assert (np.diff(c) <= 0).all()
+
+
+WORKER = r"""
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from deepblast_b200.sharding import shard_range, lpt_assign
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2],
+                        rank=int(sys.argv[3]), world_size=2)
+rank, world = dist.get_rank(), dist.get_world_size()
+B, N, M = 37, 8, 8
+lo, hi = shard_range(B, world, rank)
+cells = torch.tensor([float((hi - lo) * N * M)])
+dist.all_reduce(cells)                      # the only collective: a scalar
+assert cells.item() == B * N * M
+owned = torch.zeros(B); owned[lo:hi] = 1
+dist.all_reduce(owned)
+assert bool((owned == 1).all())             # disjoint cover
+rng = np.random.default_rng(0)
+c = rng.integers(1, 1000, size=101)
+mine = lpt_assign(c, world)[rank]
+tot = torch.tensor([float(c[mine].sum())]); dist.all_reduce(tot)
+assert tot.item() == float(c.sum())
+t = torch.tensor([1.0 + rank]); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+assert t.item() == 2.0                      # max-over-ranks timing reduction
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
