@@ -82,8 +82,9 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(const __grid_consta
     qpipe.reset();
 
     auto issue_row = [&](const Strip& st, int tq, unsigned slot) {
-        row_tile_load_generic(rtiles + slot * kTileElems, &rbars[slot], s_Zt, st.pair, st.k, tq, t);
-        row_tile_load_generic(rtiles + (kRowRing + slot) * kTileElems, &rbars[slot], s_ZA, st.pair, st.k, tq, t);
+        row_tile_load_generic(rtiles + slot * kTileElems, s_Zt, st.pair, st.k, tq, t);
+        row_tile_load_generic(rtiles + (kRowRing + slot) * kTileElems, s_ZA, st.pair, st.k, tq, t);
+        cp_async_mbar_arrive_noinc(&rbars[slot]);
     };
     // ascending sweep: tile a covers steps [16a, 16a+16) = padded diagonals 32k+2+16a ..
     auto issue_q = [&](const Strip& st, int a, unsigned slot) {
@@ -95,7 +96,8 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(const __grid_consta
                 tma_load_4d(dst, &tm_Q, &qbars[slot], (st.k + 1) * kTile, 0, dlo, st.pair);
             }
         } else {
-            diag_tile_load_generic(dst, &qbars[slot], p.Q, p.ql, st.pair, (st.k + 1) * kTile, dlo, t);
+            diag_tile_load_generic(dst, p.Q, p.ql, st.pair, (st.k + 1) * kTile, dlo, t);
+            cp_async_mbar_arrive_noinc(&qbars[slot]);
         }
     };
 
@@ -312,8 +314,9 @@ __global__ void __launch_bounds__(256) softdp_adj_bwd_kernel(const __grid_consta
                 tma_load_4d(dqd, &tm_Qd, &qbars[slot], (kb + 1) * kTile, 0, dlo, st.pair);
             }
         } else {
-            diag_tile_load_generic(dq, &qbars[slot], p.Q, p.ql, st.pair, (kb + 1) * kTile, dlo, t);
-            diag_tile_load_generic(dqd, &qbars[slot], p.Qd, p.ql, st.pair, (kb + 1) * kTile, dlo, t);
+            diag_tile_load_generic(dq, p.Q, p.ql, st.pair, (kb + 1) * kTile, dlo, t);
+            diag_tile_load_generic(dqd, p.Qd, p.ql, st.pair, (kb + 1) * kTile, dlo, t);
+            cp_async_mbar_arrive_noinc(&qbars[slot]);
         }
     };
 

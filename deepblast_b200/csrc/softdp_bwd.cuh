@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(256) softdp_bwd_kernel(const __grid_constant__
                 tma_load_4d(dst, &tm_Q, &bars[slot], (kb + 1) * kTile, 0, dlo, st.pair);
             }
         } else {
-            diag_tile_load_generic(dst, &bars[slot], p.Q, p.ql, st.pair, (kb + 1) * kTile, dlo, t);
+            diag_tile_load_generic(dst, p.Q, p.ql, st.pair, (kb + 1) * kTile, dlo, t);
+            cp_async_mbar_arrive_noinc(&bars[slot]);
         }
     };
 

@@ -53,8 +53,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// A wait that cannot complete is a protocol bug: trap (the launch fails with an error
+// the host sees) instead of hanging the device.
+constexpr unsigned kSpinLimit = 1u << 22;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) __trap();
     }
 }
 
@@ -181,10 +186,12 @@ __device__ __forceinline__ void strip_next(Strip& s, const PairDims& d, int w, i
 
 // wait until boundary `q` has published at least `need` entries
 __device__ __forceinline__ int progress_wait(const unsigned long long* word, unsigned q, int need) {
+    unsigned spins = 0;
     for (;;) {
         unsigned long long v = ld_acquire_u64(word);
         if ((unsigned)(v >> 32) == q && (int)(unsigned)v >= need) return (int)(unsigned)v;
         __nanosleep(32);
+        if (++spins > kSpinLimit) __trap();
     }
 }
 

@@ -89,8 +89,9 @@ __global__ void __launch_bounds__(256) softdp_fwd_kernel(const __grid_constant__
                 tma_load_3d(dA, &tm_A, &bars[slot], tq * kTile, st.k * kTile, st.pair);
             }
         } else {
-            row_tile_load_generic(dth, &bars[slot], s_theta, st.pair, st.k, tq, t);
-            row_tile_load_generic(dA, &bars[slot], s_A, st.pair, st.k, tq, t);
+            row_tile_load_generic(dth, s_theta, st.pair, st.k, tq, t);
+            row_tile_load_generic(dA, s_A, st.pair, st.k, tq, t);
+            cp_async_mbar_arrive_noinc(&bars[slot]);
         }
     };
 

@@ -59,8 +59,10 @@ struct RowSrc {
     int rows, cols;      // addressable extent per pair (reads beyond are zero-filled)
 };
 
-// Generic path: 32 lanes x 32 cp.async (4 B) + one noinc arrive per lane.
-__device__ __forceinline__ void row_tile_load_generic(float* dst, uint64_t* bar, const RowSrc& src, int pair, int rb,
+// Generic path: 32 lanes x 32 cp.async (4 B).  The CALLER arrives on the slot's
+// mbarrier exactly once per lane per slot (cp_async_mbar_arrive_noinc) after all the
+// tensors that share the slot have been issued.
+__device__ __forceinline__ void row_tile_load_generic(float* dst, const RowSrc& src, int pair, int rb,
                                                       int cb, int lane) {
     const float* pb = src.base + (long long)pair * src.pair_stride;
     const int col = cb * kTile + lane;
@@ -72,12 +74,11 @@ __device__ __forceinline__ void row_tile_load_generic(float* dst, uint64_t* bar,
         const float* g = ok ? (pb + (long long)row * src.pitch + col) : src.base;
         cp_async4_zfill(dst + r * kTile + lane, g, ok);
     }
-    cp_async_mbar_arrive_noinc(bar);
 }
 
 // ---- anti-diagonal-major Q tile: [kDiagRows diagonals][3 states][32 rows] -------
 // Generic path for the same box the TMA map describes.
-__device__ __forceinline__ void diag_tile_load_generic(float* dst, uint64_t* bar, const float* q, const QLayout& ql,
+__device__ __forceinline__ void diag_tile_load_generic(float* dst, const float* q, const QLayout& ql,
                                                        int pair, int ip0, int dlo, int lane) {
     const float* pb = q + (long long)pair * ql.pair_stride;
 #pragma unroll 4
@@ -90,7 +91,6 @@ __device__ __forceinline__ void diag_tile_load_generic(float* dst, uint64_t* bar
             cp_async4_zfill(dst + (dd * 3 + s) * 32 + lane, g, ok);
         }
     }
-    cp_async_mbar_arrive_noinc(bar);
 }
 
 }  // namespace b200dp

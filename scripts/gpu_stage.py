@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Staged GPU bring-up: each micro-check runs in its own subprocess with a short
+timeout, so one hung or trapped kernel costs seconds, not the whole box visit.
+usage: python scripts/gpu_stage.py [check ...]   (no args = all)"""
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHECK = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %(root)r)
+from deepblast_b200 import ops
+from oracle import softdp as O
+name, mode, B, N, M, W, flags, grid = %(spec)r
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(2)
+theta = torch.rand(B, N, M, generator=g); A = -torch.rand(B, N, M, generator=g)
+Et = torch.linspace(0.5, 1.5, B)
+Zt = torch.randn(B, N + 2, M + 2, generator=g); ZA = torch.randn(B, N, M, generator=g) * 0.1
+fl = flags | (W << 4) | (grid << 8)
+Vt_o, Q_o = O.forward_pass(theta.numpy(), A.numpy(), mode)
+E_o = O.backward_pass(Et.numpy(), Q_o, mode)
+res = {}
+if name.startswith("fwd") or name.startswith("all"):
+    Vt, Q = ops.forward_pass(theta.to(dev), A.to(dev), mode, row_borders=True, flags=fl)
+    torch.cuda.synchronize()
+    res["dVt_rel"] = float(np.abs(Vt.cpu().numpy() - Vt_o).max() / max(1.0, np.abs(Vt_o).max()))
+    res["dQ"] = float(np.abs(Q.cpu().numpy() - Q_o).max())
+else:
+    Q = ops.q_from_reference(torch.from_numpy(Q_o).to(dev))
+if name.startswith("bwd") or name.startswith("all"):
+    E = ops.backward_pass(Et.to(dev), Q, mode, flags=fl)
+    torch.cuda.synchronize()
+    res["dE"] = float(np.abs(E.cpu().numpy() - E_o).max())
+if name.startswith("adj") or name.startswith("all"):
+    Qr = ops.q_from_reference(torch.from_numpy(Q_o).to(dev))
+    Vtd_o, Qd_o = O.adjoint_forward_pass(Q_o, Zt.numpy(), ZA.numpy())
+    Ed_o = O.adjoint_backward_pass(E_o, Q_o, Qd_o)
+    Vtd, Qd = ops.adjoint_forward_pass(Qr, Zt.to(dev), ZA.to(dev), flags=fl)
+    torch.cuda.synchronize()
+    sc = max(1.0, float(np.abs(Vtd_o).max()))
+    res["dVtd_rel"] = float(np.abs(Vtd.cpu().numpy() - Vtd_o).max() / sc)
+    res["dQd_rel"] = float(np.abs(Qd[:, 1:-1, 1:-1].cpu().numpy() - Qd_o[:, 1:-1, 1:-1]).max() / sc)
+    Ed = ops.adjoint_backward_pass(torch.from_numpy(E_o).to(dev), Qr, Qd, flags=fl)
+    torch.cuda.synchronize()
+    res["dEd_rel"] = float(np.abs(Ed.cpu().numpy() - Ed_o).max() / max(1.0, float(np.abs(Ed_o).max())))
+bad = [k for k, v in res.items() if not (v < 1e-4)]
+print(("FAIL " if bad else "PASS ") + " ".join("%%s=%%.2e" %% kv for kv in res.items()))
+'''
+
+NO_TMA = 2
+SPECS = [
+    # name, mode, B, N, M, W, flags, grid
+    ("fwd_tma_64", "nw", 2, 64, 64, 1, 0, 0),
+    ("fwd_gen_64", "nw", 2, 64, 64, 1, NO_TMA, 0),
+    ("bwd_tma_64", "nw", 2, 64, 64, 1, 0, 0),
+    ("bwd_gen_64", "nw", 2, 64, 64, 1, NO_TMA, 0),
+    ("adj_tma_64", "nw", 2, 64, 64, 1, 0, 0),
+    ("adj_gen_64", "nw", 2, 64, 64, 1, NO_TMA, 0),
+    ("all_tma_5x4", "nw", 3, 5, 4, 1, 0, 0),
+    ("all_tma_w2_200", "nw", 3, 200, 152, 2, 0, 0),
+    ("all_tma_w4_200", "sw", 3, 200, 152, 4, 0, 0),
+    ("all_tma_w8_300", "nw", 2, 300, 77, 8, 0, 0),
+    ("all_gen_w2_grid", "nw", 13, 70, 90, 2, NO_TMA, 3),
+    ("all_tma_w1_grid", "sw", 13, 96, 128, 1, 0, 3),
+    ("all_tma_256", "nw", 4, 256, 256, 0, 0, 0),
+    ("all_tma_1024", "nw", 1, 1024, 1024, 0, 0, 0),
+]
+
+
+def main():
+    want = sys.argv[1:]
+    for spec in SPECS:
+        if want and not any(w in spec[0] for w in want):
+            continue
+        code = CHECK % dict(root=ROOT, spec=spec)
+        t0 = time.time()
+        try:
+            p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=90)
+            out = (p.stdout.strip().splitlines() or ["(no stdout)"])[-1]
+            if p.returncode != 0:
+                out = "ERROR rc=%d %s | %s" % (p.returncode, out, p.stderr.strip().splitlines()[-1:] )
+        except subprocess.TimeoutExpired:
+            out = "TIMEOUT (hang)"
+        print("%-18s %5.1fs  %s" % (spec[0], time.time() - t0, out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
