@@ -158,6 +158,17 @@ int pick_geometry(const char* fn, int B, int N, int M, int flags, SmemFn smem_of
             g.smem = smem;
         }
     }
+    if (!g.W && forceW) {
+        // the requested warps-per-pair does not fit in shared memory: take the largest that does
+        for (int W = forceW / 2; W >= 1 && !g.W; W /= 2) {
+            size_t smem = smem_of(W, M);
+            if (smem > (size_t)di.smem_optin) continue;
+            g.W = W;
+            g.smem = smem;
+            long long resident = (long long)di.sms * (long long)((size_t)di.smem_per_sm / (smem + 1024) ? (size_t)di.smem_per_sm / (smem + 1024) : 1);
+            g.grid = (int)(B < resident ? B : resident);
+        }
+    }
     if (!g.W) return fail(-3, std::string(fn) + ": M too large for shared memory boundary rows");
     if (forceG > 0) g.grid = forceG;
     return 0;
