@@ -12,7 +12,9 @@
 #include "../../include/b200dp.h"
 #include "softdp_adjoint.cuh"
 #include "softdp_bwd.cuh"
+#include "softdp_bwd2.cuh"
 #include "softdp_fwd.cuh"
+#include "softdp_fwd2.cuh"
 #include "softdp_traceback.cuh"
 
 using namespace b200dp;
@@ -75,12 +77,12 @@ bool dev_info(DevInfo& out) {
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // rank-3 map over a contiguous [B, N, M] fp32 tensor, box 32 cols x 32 rows x 1
-bool encode_row_map(CUtensorMap* map, const float* ptr, int B, int N, int M) {
+bool encode_row_map(CUtensorMap* map, const float* ptr, int B, int N, int M, int boxdim = kTile) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)M, (cuuint64_t)N, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)M * 4, (cuuint64_t)N * M * 4};
-    cuuint32_t box[3] = {kTile, kTile, 1};
+    cuuint32_t box[3] = {(cuuint32_t)boxdim, (cuuint32_t)boxdim, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -102,9 +104,19 @@ bool encode_q_map(CUtensorMap* map, const float* ptr, int B, const QLayout& ql) 
     return r == CUDA_SUCCESS;
 }
 
+// Row pitch of the anti-diagonal-major layout: at least N + 33 floats, a multiple of 32;
+// taken from a small fixed set where possible so the fast kernels can be instantiated
+// with the pitch as a compile-time constant.
+constexpr int kLpSet[] = {128, 320, 576, 1088, 2112};
+
 QLayout q_layout(int N, int M) {
     QLayout ql;
     ql.Lp = ((N + 33 + 31) / 32) * 32;
+    for (int lp : kLpSet)
+        if (lp >= N + 33) {
+            ql.Lp = lp;
+            break;
+        }
     ql.ND = N + M + 3;
     ql.pair_stride = (long long)ql.ND * 3 * ql.Lp;
     return ql;
@@ -185,6 +197,12 @@ bool env_no_tma() {
     const char* e = getenv("B200DP_NO_TMA");
     return e && atoi(e) != 0;
 }
+// B200DP_V1=1 (or flag B200DP_V1_KERNELS) keeps the general kernels on shapes the fast
+// path would take; used by the parity tests to cover both.
+bool env_v1() {
+    const char* e = getenv("B200DP_V1");
+    return e && atoi(e) != 0;
+}
 
 }  // namespace
 
@@ -228,6 +246,29 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
     memset(&tmA, 0, sizeof(tmA));
     bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma() && (M % 4 == 0) && M >= kTile && N >= kTile &&
                aligned(theta, 16) && aligned(A, 16);
+    const bool fast = tma && !(flags & B200DP_V1_KERNELS) && !env_v1() && N >= kG && M >= 2 * kG;
+    if (fast && encode_row_map(&tmT, theta, B, N, M, kG) && encode_row_map(&tmA, A, B, N, M, kG)) {
+        Geometry g2;
+        if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes, g2)) return rc;
+        int rc2 = 0;
+        auto launch = [&](auto kern) {
+            rc2 = set_smem(kern, g2.smem, "b200dp_fwd");
+            if (!rc2) kern<<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmT, tmA, p);
+        };
+        const bool sw = mode == B200DP_MODE_SW;
+        switch (p.ql.Lp) {
+            case 128: sw ? launch(softdp_fwd2_kernel<true, 128>) : launch(softdp_fwd2_kernel<false, 128>); break;
+            case 320: sw ? launch(softdp_fwd2_kernel<true, 320>) : launch(softdp_fwd2_kernel<false, 320>); break;
+            case 576: sw ? launch(softdp_fwd2_kernel<true, 576>) : launch(softdp_fwd2_kernel<false, 576>); break;
+            case 1088: sw ? launch(softdp_fwd2_kernel<true, 1088>) : launch(softdp_fwd2_kernel<false, 1088>); break;
+            case 2112: sw ? launch(softdp_fwd2_kernel<true, 2112>) : launch(softdp_fwd2_kernel<false, 2112>); break;
+            default: sw ? launch(softdp_fwd2_kernel<true, 0>) : launch(softdp_fwd2_kernel<false, 0>); break;
+        }
+        if (rc2) return rc2;
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) return cuda_fail(e2, "b200dp_fwd launch");
+        return 0;
+    }
     if (tma) tma = encode_row_map(&tmT, theta, B, N, M) && encode_row_map(&tmA, A, B, N, M);
     if (tma) {
         if (int rc = set_smem(softdp_fwd_kernel<true>, g.smem, "b200dp_fwd")) return rc;
@@ -264,6 +305,20 @@ int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E, c
     memset(&tmQ, 0, sizeof(tmQ));
     bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma();
     if (tma) tma = encode_q_map(&tmQ, Q, B, p.ql);
+    if (tma && !(flags & B200DP_V1_KERNELS) && !env_v1() && M >= 2 * kG) {
+        Geometry g2;
+        if (int rc = pick_geometry("b200dp_bwd", B, N, M, flags, bwd2_smem_bytes, g2)) return rc;
+        if (mode == B200DP_MODE_SW) {
+            if (int rc = set_smem(softdp_bwd2_kernel<true>, g2.smem, "b200dp_bwd")) return rc;
+            softdp_bwd2_kernel<true><<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmQ, p);
+        } else {
+            if (int rc = set_smem(softdp_bwd2_kernel<false>, g2.smem, "b200dp_bwd")) return rc;
+            softdp_bwd2_kernel<false><<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmQ, p);
+        }
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) return cuda_fail(e2, "b200dp_bwd launch");
+        return 0;
+    }
     if (tma) {
         if (int rc = set_smem(softdp_bwd_kernel<true>, g.smem, "b200dp_bwd")) return rc;
         softdp_bwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, p);

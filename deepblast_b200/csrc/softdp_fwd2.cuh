@@ -1,0 +1,272 @@
+// softdp_fwd2.cuh -- forward fill, fast path (reference: deepblast/nw.py:46-62,
+// sw.py:46-62; replaces deepblast/nw_cuda.py:46-79).
+//
+// Same wavefront as softdp_fwd.cuh (lane t owns row 32k+t+1, one column per step,
+// V carried as an fp32 (hi, lo) pair, Q written anti-diagonal-major, one 128-byte line
+// per state per step) re-organised for instruction count and occupancy:
+//   * steps run in blocks of 16; blocks in which every lane is inside the lattice are
+//     fully unrolled with no per-lane predicates ("steady"), the ramps use the
+//     predicated variant of the same step ("edge");
+//   * theta/A are staged by TMA as 16x16 boxes for two 16-row groups per warp; group 1
+//     trails group 0 by one tile, so the live window is a parallelogram and the ring is
+//     12 KB per warp (3 events x {2 groups x 2 tensors x 1 KB});
+//   * tile waits, boundary-row progress and ring bookkeeping happen once per block.
+#pragma once
+#include "softdp_fwd.cuh"
+
+namespace b200dp {
+
+constexpr int kG = 16;                       // rows per group == columns per tile
+constexpr int kF2Ring = 3;                   // events resident: 2 live + 1 in flight
+constexpr int kF2SlotBytes = 4096;           // [2 groups][2 tensors][16][16] fp32
+constexpr int kF2WarpBytes = kF2Ring * kF2SlotBytes;
+
+__host__ __device__ inline size_t fwd2_smem_bytes(int W, int M) {
+    size_t b = (size_t)W * kF2WarpBytes;
+    b += (size_t)W * kF2Ring * 8;
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)(W + 1) * 8;
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)(W + 1) * (size_t)M * 8;
+    b += 128;                                      // 16 zero (hi, lo) pairs
+    return b;
+}
+
+// One wavefront step of one lane.  EDGE adds the lattice-membership predicates and the
+// zero border cells; SWM adds the sw.py i, j >= 2 rule.  All state by reference.
+template <bool EDGE, bool SWM>
+__device__ __forceinline__ void fwd2_step(float th, float a, float uh, float ul, float& vh, float& vl, float& dh,
+                                          float& dl, float* __restrict__ qp, int Lp, bool store, bool comp) {
+    // u_x - u_m and u_y - u_m (nw.py:56-58) from the (hi, lo) pairs
+    const float dx = ((uh - dh) + (ul - dl)) + a;
+    const float dy = ((vh - dh) + (vl - dl)) + a;
+    const float mx = fmaxf(fmaxf(dx, dy), 0.f);
+    const float mxs = mx * kLog2e;
+    const float ex = fast_ex2(fmaf(dx, kLog2e, -mxs));
+    const float ey = fast_ex2(fmaf(dy, kLog2e, -mxs));
+    const float em = fast_ex2(-mxs);
+    const float S = (ex + em) + ey;
+    const float r = fast_rcp(S);
+    float qx = ex * r, qm = em * r, qy = ey * r;
+    // V[i,j] = V[i-1,j-1] + (theta + logsumexp(dx, 0, dy))   (nw.py:59-60), Fast2Sum
+    const float delta = th + fmaf(fast_lg2(S), kLn2, mx);
+    const float t1 = delta + dl;
+    float nh = dh + t1;
+    float nl = t1 - (nh - dh);
+    if (EDGE || SWM) {
+        if (!comp) {
+            qx = qm = qy = 0.f;
+            nh = nl = 0.f;
+        }
+    }
+    if (!EDGE || store) {
+        qp[0] = qx;
+        qp[Lp] = qm;
+        qp[2 * Lp] = qy;
+    }
+    dh = uh;
+    dl = ul;
+    vh = nh;
+    vl = nl;
+}
+
+// LP > 0 fixes the Q row pitch at compile time (b200dp_q_layout picks it from a small
+// set), so every Q store of an unrolled block is base + immediate; LP = 0 reads it
+// from the parameters.
+template <bool SWM, int LP>
+__global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant__ CUtensorMap tm_theta,
+                                                          const __grid_constant__ CUtensorMap tm_A, FwdParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int W = blockDim.x >> 5, w = threadIdx.x >> 5, t = threadIdx.x & 31;
+    const int NB = W + 1;
+    const int Mcap = p.d.M;
+    const int g = t >> 4, tp = t & 15;
+
+    unsigned char* ring = smem_raw + (size_t)w * kF2WarpBytes;
+    size_t off = (size_t)W * kF2WarpBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + off) + w * kF2Ring;
+    off += (size_t)W * kF2Ring * 8;
+    off = (off + 15) & ~(size_t)15;
+    unsigned long long* prog = reinterpret_cast<unsigned long long*>(smem_raw + off);
+    off += (size_t)NB * 8;
+    off = (off + 15) & ~(size_t)15;
+    float2* bnd = reinterpret_cast<float2*>(smem_raw + off);
+
+    if (t == 0) {
+        for (int s = 0; s < kF2Ring; ++s) mbar_init(&bars[s], 1);
+    }
+    if ((int)threadIdx.x < NB) prog[threadIdx.x] = ~0ull;
+    fence_mbar_init();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_theta);
+        tma_prefetch_desc(&tm_A);
+    }
+
+    const int Lp = LP ? LP : p.ql.Lp;
+    const int dstep = 3 * Lp;
+    const bool borders = (p.flags & 1) != 0;
+    // lane-constant part of the tile address: group, row, and the -4*tp column skew
+    const int lanebase = g * 2048 + tp * 60;
+    // 16 zero (hi, lo) pairs: the "row above" of a pair's first strip
+    float2* zero_row = bnd + (size_t)NB * Mcap;
+    if (threadIdx.x < 16) zero_row[threadIdx.x] = make_float2(0.f, 0.f);
+    __syncthreads();
+
+    Strip cur, nxt;
+    strip_first(cur, p.d, w, W);
+    nxt = cur;
+    if (cur.valid) strip_next(nxt, p.d, w, W);
+
+    TilePipe<kF2Ring, kF2Ring - 2> pipe;
+    pipe.reset();
+
+    // event e of a strip = {group 0: tile e, group 1: tile e-1} x {theta, A}
+    auto issue = [&](const Strip& st, int e, unsigned slot) {
+        if (t == 0) {
+            const int T16 = (st.m + kG - 1) / kG;
+            unsigned char* dst = ring + slot * kF2SlotBytes;
+            const bool g0 = e < T16, g1 = e >= 1;
+            mbar_expect_tx(&bars[slot], (g0 ? 2048u : 0u) + (g1 ? 2048u : 0u));
+            if (g0) {
+                tma_load_3d(dst, &tm_theta, &bars[slot], e * kG, st.k * kTile, st.pair);
+                tma_load_3d(dst + 1024, &tm_A, &bars[slot], e * kG, st.k * kTile, st.pair);
+            }
+            if (g1) {
+                tma_load_3d(dst + 2048, &tm_theta, &bars[slot], (e - 1) * kG, st.k * kTile + kG, st.pair);
+                tma_load_3d(dst + 3072, &tm_A, &bars[slot], (e - 1) * kG, st.k * kTile + kG, st.pair);
+            }
+        }
+    };
+
+    while (cur.valid) {
+        const int n = cur.n, m = cur.m, k = cur.k;
+        const int T16 = (m + kG - 1) / kG;
+        const int NE = T16 + 1;                       // events of this strip
+        const int NEn = nxt.valid ? (nxt.m + kG - 1) / kG + 1 : 0;
+        const int NBk = (m + 32 + 15) / 16;           // blocks: steps s' = 0 .. m+31
+        const int i = k * kTile + t + 1;
+        const bool row_ok = i <= n;
+        const bool rowcomp = row_ok && i >= p.i0;
+        const bool full_rows = (k + 1) * kTile <= n;
+        const bool has_up = k > 0;
+        const bool feeds_down = (k + 1 < cur.K);
+        const unsigned q = cur.q;
+        const float2* bnd_r = bnd + (size_t)((q + NB - 1) % NB) * Mcap;
+        float2* bnd_w = bnd + (size_t)(q % NB) * Mcap;
+        const unsigned long long* prog_r = prog + ((q + NB - 1) % NB);
+        unsigned long long* prog_w = prog + (q % NB);
+
+        float vh = 0.f, vl = 0.f, dh = 0.f, dl = 0.f;
+        // cell (i, j = c+1), c = s' - t, sits on padded diagonal 32k + 2 + s'
+        float* qp = p.Q + (long long)cur.pair * p.ql.pair_stride + (long long)(k * kTile + 1) * dstep +
+                    (k + 1) * kTile + t;
+        float2* bw31 = bnd_w - 31;
+
+        // prologue step s' = -1: lane 0's zero border cell (i, 0)
+        if (t == 0 && row_ok) {
+            qp[0] = 0.f;
+            qp[Lp] = 0.f;
+            qp[2 * Lp] = 0.f;
+            if (borders && i == 1) {                  // cells (0, 0) and (0, 1)
+                qp[-1] = 0.f; qp[Lp - 1] = 0.f; qp[2 * Lp - 1] = 0.f;
+                float* q0 = qp - dstep;
+                q0[-1] = 0.f; q0[Lp - 1] = 0.f; q0[2 * Lp - 1] = 0.f;
+            }
+        }
+        qp += dstep;
+
+        int avail = 0;
+        unsigned slotA = 0, slotB = 0;
+        for (int b = 0; b < NBk; ++b) {
+            __syncwarp();
+            slotA = slotB;
+            if (b < NE) {
+                pipe.pump(b, NE, nxt.valid, NEn,
+                          [&](bool from_next, int e, unsigned slot) { issue(from_next ? nxt : cur, e, slot); });
+                slotB = pipe.wait(bars);
+            }
+            const int s0 = b * 16;
+            if (W > 1 && has_up && s0 < m) {
+                const int need = min(s0 + 16, m);
+                if (avail < need) avail = progress_wait(prog_r, q - 1, need);
+            }
+            const float* baseA = reinterpret_cast<const float*>(ring + slotA * kF2SlotBytes + lanebase + 64);
+            const float* baseB = reinterpret_cast<const float*>(ring + slotB * kF2SlotBytes + lanebase);
+            const bool steady = full_rows && b >= 2 && s0 + 16 <= m && !(SWM && k == 0) && !borders;
+            if (steady) {
+                const float2* br = has_up ? bnd_r + s0 : zero_row;
+                float2* bw = bw31 + s0;
+#pragma unroll
+                for (int ss = 0; ss < 16; ++ss) {
+                    float uh = __shfl_up_sync(kFull, vh, 1);
+                    float ul = __shfl_up_sync(kFull, vl, 1);
+                    if (t == 0) {
+                        const float2 bv = br[ss];
+                        uh = bv.x;
+                        ul = bv.y;
+                    }
+                    const float* tb = (tp <= ss) ? baseB : baseA;
+                    const float th = tb[ss];
+                    const float a = tb[ss + 256];
+                    fwd2_step<false, false>(th, a, uh, ul, vh, vl, dh, dl, qp + ss * dstep, Lp, true, true);
+                    if (t == 31 && feeds_down) bw[ss] = make_float2(vh, vl);
+                }
+                qp += 16 * dstep;
+            } else {
+#pragma unroll 4
+                for (int ss = 0; ss < 16; ++ss) {
+                    const int sp = s0 + ss;           // s'
+                    const int c = sp - t;
+                    float uh = __shfl_up_sync(kFull, vh, 1);
+                    float ul = __shfl_up_sync(kFull, vl, 1);
+                    if (t == 0) {
+                        uh = 0.f;
+                        ul = 0.f;
+                        if (has_up && c < m) {
+                            const float2 bv = bnd_r[c];
+                            uh = bv.x;
+                            ul = bv.y;
+                        }
+                    }
+                    const bool in = row_ok && c >= 0 && c < m;
+                    const bool comp = in && rowcomp && (c + 1) >= p.i0;
+                    const bool store = row_ok && c >= -1 && c <= m;
+                    float th = 0.f, a = 0.f;
+                    if (in) {
+                        const float* tb = (tp <= ss) ? baseB : baseA;
+                        th = tb[ss];
+                        a = tb[ss + 256];
+                    }
+                    fwd2_step<true, SWM>(th, a, uh, ul, vh, vl, dh, dl, qp, Lp, store, comp);
+                    if (store && borders) {
+                        if (i == 1 && c + 1 <= m) {   // cell (0, c+2) shares this diagonal
+                            qp[-1] = 0.f; qp[Lp - 1] = 0.f; qp[2 * Lp - 1] = 0.f;
+                        }
+                        if (i == n && c >= 0) {       // cell (n+1, c)
+                            qp[1] = 0.f; qp[Lp + 1] = 0.f; qp[2 * Lp + 1] = 0.f;
+                        }
+                    }
+                    if (t == 31 && feeds_down && in) bnd_w[c] = make_float2(vh, vl);
+                    if (in && i == n && c == m - 1) p.Vt[cur.pair] = vh + vl;
+                    qp += dstep;
+                }
+            }
+            if (W > 1 && feeds_down && t == 31) {
+                const int done = min(max(s0 + 16 - 31, 0), m);
+                if (done > 0) st_release_u64(prog_w, ((unsigned long long)q << 32) | (unsigned)done);
+            }
+        }
+        if (borders && i == n) {                      // Q[n+1, m+1, :] = 1 (nw.py:51)
+            float* qc = p.Q + (long long)cur.pair * p.ql.pair_stride + 31 + (long long)(n + m + 2) * dstep + (n + 1);
+            qc[0] = 1.f;
+            qc[Lp] = 1.f;
+            qc[2 * Lp] = 1.f;
+        }
+        pipe.next_strip(NE);
+        cur = nxt;
+        if (cur.valid) strip_next(nxt, p.d, w, W);
+    }
+}
+
+}  // namespace b200dp

@@ -43,6 +43,7 @@ extern "C" {
 /* flags */
 #define B200DP_Q_ROW_BORDERS 0x1   /* fwd: also write Q[0,:,:], Q[n+1,:,:] (zeros, corner = 1) */
 #define B200DP_NO_TMA        0x2   /* stage tiles with cp.async instead of TMA (debug / unaligned) */
+#define B200DP_V1_KERNELS    0x4   /* use the general kernels even where the fast path applies */
 #define B200DP_WARPS_SHIFT   4     /* bits 4..7: warps per pair (1,2,4,8); 0 = choose automatically */
 #define B200DP_CTAS_SHIFT    8     /* bits 8..23: grid size override; 0 = choose automatically */
 

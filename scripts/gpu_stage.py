@@ -29,6 +29,10 @@ if name.startswith("fwd") or name.startswith("all"):
     torch.cuda.synchronize()
     res["dVt_rel"] = float(np.abs(Vt.cpu().numpy() - Vt_o).max() / max(1.0, np.abs(Vt_o).max()))
     res["dQ"] = float(np.abs(Q.cpu().numpy() - Q_o).max())
+    Vt, Q = ops.forward_pass(theta.to(dev), A.to(dev), mode, row_borders=False, flags=fl)
+    torch.cuda.synchronize()
+    res["dVt2_rel"] = float(np.abs(Vt.cpu().numpy() - Vt_o).max() / max(1.0, np.abs(Vt_o).max()))
+    res["dQ2"] = float(np.abs(Q[:, 1:-1].cpu().numpy() - Q_o[:, 1:-1]).max())
 else:
     Q = ops.q_from_reference(torch.from_numpy(Q_o).to(dev))
 if name.startswith("bwd") or name.startswith("all"):
@@ -52,9 +56,22 @@ print(("FAIL " if bad else "PASS ") + " ".join("%%s=%%.2e" %% kv for kv in res.i
 '''
 
 NO_TMA = 2
+V1 = 4
 SPECS = [
+    ("fwd_v2_64", "nw", 2, 64, 64, 1, 0, 0),
+    ("bwd_v2_64", "nw", 2, 64, 64, 1, 0, 0),
+    ("all_v2_256", "nw", 4, 256, 256, 0, 0, 0),
+    ("all_v2_sw_256", "sw", 4, 256, 256, 0, 0, 0),
+    ("all_v2_w2_200", "nw", 3, 200, 152, 2, 0, 0),
+    ("all_v2_w4_300", "sw", 2, 300, 100, 4, 0, 0),
+    ("all_v2_grid", "nw", 13, 70, 92, 2, 0, 3),
+    ("all_v2_w1_grid", "sw", 13, 96, 128, 1, 0, 3),
+    ("all_v2_1024", "nw", 1, 1024, 1024, 0, 0, 0),
+    ("all_v2_520", "nw", 2, 130, 520, 0, 0, 0),
+]
+SPECS_V1 = [
     # name, mode, B, N, M, W, flags, grid
-    ("fwd_tma_64", "nw", 2, 64, 64, 1, 0, 0),
+    ("fwd_tma_64", "nw", 2, 64, 64, 1, V1, 0),
     ("fwd_gen_64", "nw", 2, 64, 64, 1, NO_TMA, 0),
     ("bwd_tma_64", "nw", 2, 64, 64, 1, 0, 0),
     ("bwd_gen_64", "nw", 2, 64, 64, 1, NO_TMA, 0),
@@ -73,7 +90,7 @@ SPECS = [
 
 def main():
     want = sys.argv[1:]
-    for spec in SPECS:
+    for spec in SPECS + SPECS_V1:
         if want and not any(w in spec[0] for w in want):
             continue
         code = CHECK % dict(root=ROOT, spec=spec)

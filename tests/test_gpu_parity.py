@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 CASES = ["t_nw_cuda_5x5", "t_nw_4x4", "r8x8", "r17x23", "r33x40", "r64x48", "r40x70"]
 ATOL_QE = 1e-5
 NO_TMA = 0x2
+V1 = 0x4          # general kernels even where the fast path applies
 
 
 def dev():
@@ -80,30 +81,42 @@ SHAPES = [(2, 1, 1), (2, 1, 9), (2, 9, 1), (3, 31, 33), (2, 32, 32), (2, 64, 64)
           (2, 96, 200), (1, 256, 193), (2, 256, 256), (1, 300, 77), (1, 130, 520)]
 
 
-@pytest.mark.parametrize("B,N,M", SHAPES)
-@pytest.mark.parametrize("mode", ["nw", "sw"])
-@pytest.mark.parametrize("flags", [0, NO_TMA])
-def test_seeded_vs_oracle(ops, B, N, M, mode, flags):
-    theta, A = rand_inputs(B, N, M)
+def check_fwd_bwd(ops, theta, A, Et, mode, flags):
+    """Forward + backward against the oracle, with and without Q's row borders (the
+    fast kernels only run their unrolled blocks without them)."""
     Vt_o, Q_o = O.forward_pass(theta.numpy(), A.numpy(), mode)
-    Et = torch.linspace(0.5, 1.5, B)
     E_o = O.backward_pass(Et.numpy(), Q_o, mode)
-    Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), mode, row_borders=True, flags=flags)
+    th, a = theta.to(dev()), A.to(dev())
+    Vt, Q = ops.forward_pass(th, a, mode, row_borders=True, flags=flags)
     np.testing.assert_allclose(Vt.cpu().numpy(), Vt_o, rtol=1e-6)
     np.testing.assert_allclose(Q.cpu().numpy(), Q_o, rtol=0, atol=ATOL_QE)
-    E = ops.backward_pass(Et.to(dev()), Q, mode, flags=flags)
-    np.testing.assert_allclose(E.cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
+    Vt2, Q2 = ops.forward_pass(th, a, mode, row_borders=False, flags=flags)
+    np.testing.assert_allclose(Vt2.cpu().numpy(), Vt_o, rtol=1e-6)
+    # rows 1..N with their zero column borders j = 0 and j = M+1
+    np.testing.assert_allclose(Q2[:, 1:-1].cpu().numpy(), Q_o[:, 1:-1], rtol=0, atol=ATOL_QE)
+    for q in (Q, Q2):
+        E = ops.backward_pass(Et.to(dev()), q, mode, flags=flags)
+        np.testing.assert_allclose(E.cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
+
+
+@pytest.mark.parametrize("B,N,M", SHAPES)
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+@pytest.mark.parametrize("flags", [0, NO_TMA, V1])
+def test_seeded_vs_oracle(ops, B, N, M, mode, flags):
+    theta, A = rand_inputs(B, N, M)
+    check_fwd_bwd(ops, theta, A, torch.linspace(0.5, 1.5, B), mode, flags)
 
 
 @pytest.mark.parametrize("W", [1, 2, 4, 8])
 @pytest.mark.parametrize("mode", ["nw", "sw"])
-def test_warps_per_pair(ops, W, mode):
+@pytest.mark.parametrize("kern", [0, V1])
+def test_warps_per_pair(ops, W, mode, kern):
     """Every cross-warp hand-off configuration gives the same answer."""
-    B, N, M = 3, 200, 150
+    B, N, M = 3, 200, 152
     theta, A = rand_inputs(B, N, M, seed=5)
     Vt_o, Q_o = O.forward_pass(theta.numpy(), A.numpy(), mode)
     E_o = O.backward_pass(np.ones(B, np.float32), Q_o, mode)
-    fl = W << 4
+    fl = (W << 4) | kern
     Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), mode, flags=fl)
     E = ops.backward_pass(torch.ones(B, device=dev()), Q, mode, flags=fl)
     np.testing.assert_allclose(Vt.cpu().numpy(), Vt_o, rtol=1e-6)
@@ -123,12 +136,12 @@ def test_warps_per_pair(ops, W, mode):
 
 def test_persistent_grid_many_pairs_per_cta(ops):
     """Fewer CTAs than pairs: the strip sequence runs across pair boundaries."""
-    B, N, M = 13, 70, 90
+    B, N, M = 13, 70, 92
     theta, A = rand_inputs(B, N, M, seed=11)
     Vt_o, Q_o = O.forward_pass(theta.numpy(), A.numpy(), "nw")
     E_o = O.backward_pass(np.ones(B, np.float32), Q_o, "nw")
-    for W in (1, 2):
-        fl = (W << 4) | (3 << 8)          # 3 CTAs for 13 pairs
+    for W, kern in ((1, 0), (2, 0), (1, V1), (2, V1)):
+        fl = (W << 4) | (3 << 8) | kern   # 3 CTAs for 13 pairs
         Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), "nw", flags=fl)
         E = ops.backward_pass(torch.ones(B, device=dev()), Q, "nw", flags=fl)
         np.testing.assert_allclose(Vt.cpu().numpy(), Vt_o, rtol=1e-6)
