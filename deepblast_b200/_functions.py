@@ -22,7 +22,11 @@ def make_classes(mode, prefix):
                 raise NotImplementedError(
                     "CUDA variant only supports 'softmax' operator")
             lens = getattr(Q, "_b200dp_lens", (None, None))
-            E = ops.backward_pass(Et, Q, mode, lens[0], lens[1])
+            # Q: the engine's strip-major view (from our forward) or a dense
+            # reference-layout [B,N+2,M+2,3] tensor (converted on the fly)
+            if Q.dim() == 4:
+                Q = ops.q_from_reference(Q)
+            E = ops.backward_pass(Et, Q, mode, lens[0], lens[1], N=theta.shape[1])
             ctx.save_for_backward(Q, E)
             ctx.others = operator
             ctx.lens = lens

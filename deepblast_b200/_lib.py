@@ -15,8 +15,8 @@ _ll = ctypes.c_longlong
 EXPORTS = {
     "b200dp_version": (ctypes.c_int, []),
     "b200dp_last_error": (ctypes.c_char_p, []),
-    "b200dp_q_layout": (ctypes.c_int, [_i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i),
-                                       ctypes.POINTER(_ll), ctypes.POINTER(_i)]),
+    "b200dp_q_layout": (ctypes.c_int, [_i, _i, ctypes.POINTER(_i), ctypes.POINTER(_ll),
+                                       ctypes.POINTER(_ll), ctypes.POINTER(_ll)]),
     "b200dp_fwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "b200dp_bwd": (ctypes.c_int, [_f, _ll, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "b200dp_adj_fwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f]),
@@ -48,8 +48,9 @@ def check(rc, what):
 
 
 def q_layout(N, M):
-    Lp, ND, off = _i(), _i(), _i()
-    ps = _ll()
-    check(lib().b200dp_q_layout(N, M, ctypes.byref(Lp), ctypes.byref(ND),
-                                ctypes.byref(ps), ctypes.byref(off)), "b200dp_q_layout")
-    return Lp.value, ND.value, ps.value, off.value
+    """(K strips per pair, strip_stride, pair_stride, tail pad) in floats."""
+    K = _i()
+    ss, ps, pad = _ll(), _ll(), _ll()
+    check(lib().b200dp_q_layout(N, M, ctypes.byref(K), ctypes.byref(ss), ctypes.byref(ps),
+                                ctypes.byref(pad)), "b200dp_q_layout")
+    return K.value, ss.value, ps.value, pad.value

@@ -7,18 +7,18 @@
 // Ztheta and E are padded row-major tensors whose row pitch (M+2)*4 B is not a
 // multiple of 16 B, so they cannot be described by a TMA tensor map; their 32x32
 // tiles are staged with 4-byte cp.async on the same mbarriers.  Q and Qd are
-// anti-diagonal-major and arrive by TMA.
+// strip-major and arrive by 1-D bulk TMA, 6 KB per copy.
 #pragma once
 #include "softdp_pipes.cuh"
 
 namespace b200dp {
 
 struct AdjFwdParams {
-    const float* Q;        // diagonal-major
+    const float* Q;        // strip-major
     const float* Ztheta;   // [B, N+2, M+2]
     const float* ZA;       // [B, N, M]
     float* Vtd;            // [B]
-    float* Qd;             // diagonal-major (interior cells only are written)
+    float* Qd;             // strip-major
     PairDims d;
     QLayout ql;
 };
@@ -36,8 +36,7 @@ __host__ __device__ inline size_t adj_fwd_smem_bytes(int W, int M) {
 }
 
 template <bool kTMA>
-__global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(const __grid_constant__ CUtensorMap tm_Q,
-                                                             AdjFwdParams p) {
+__global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(AdjFwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int W = blockDim.x >> 5, w = threadIdx.x >> 5, t = threadIdx.x & 31;
     const int NB = W + 1;
@@ -63,14 +62,10 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(const __grid_consta
     if ((int)threadIdx.x < NB) prog[threadIdx.x] = ~0ull;
     fence_mbar_init();
     __syncthreads();
-    if (kTMA && threadIdx.x == 0) tma_prefetch_desc(&tm_Q);
 
     // lattice cell (r, c) 0-based of Ztheta is padded element (r+1, c+1)
     const RowSrc s_Zt{p.Ztheta + (M + 2) + 1, (long long)(N + 2) * (M + 2), M + 2, N, M};
     const RowSrc s_ZA{p.ZA, (long long)N * M, M, N, M};
-    const int Lp = p.ql.Lp;
-    const long long dstep = 3ll * Lp;
-
     Strip cur, nxt;
     strip_first(cur, p.d, w, W);
     nxt = cur;
@@ -86,19 +81,11 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(const __grid_consta
         row_tile_load_generic(rtiles + (kRowRing + slot) * kTileElems, s_ZA, st.pair, st.k, tq, t);
         cp_async_mbar_arrive_noinc(&rbars[slot]);
     };
-    // ascending sweep: tile a covers steps [16a, 16a+16) = padded diagonals 32k+2+16a ..
+    // ascending sweep: step s IS wavefront step sigma = s; tile a = sigma in [16a, 16a+16)
     auto issue_q = [&](const Strip& st, int a, unsigned slot) {
-        const int dlo = st.k * kTile + 2 + kDiagRows * a;
-        float* dst = qring + slot * kDiagElems;
-        if (kTMA) {
-            if (t == 0) {
-                mbar_expect_tx(&qbars[slot], kDiagElems * 4);
-                tma_load_4d(dst, &tm_Q, &qbars[slot], (st.k + 1) * kTile, 0, dlo, st.pair);
-            }
-        } else {
-            diag_tile_load_generic(dst, p.Q, p.ql, st.pair, (st.k + 1) * kTile, dlo, t);
-            cp_async_mbar_arrive_noinc(&qbars[slot]);
-        }
+        const float* strip = p.Q + (long long)st.pair * p.ql.pair_stride + (long long)st.k * p.ql.strip_stride;
+        q_tile_load<kTMA>(qring + slot * kDiagElems, &qbars[slot], strip, kDiagRows * a, t);
+        if (!kTMA) cp_async_mbar_arrive_noinc(&qbars[slot]);
     };
 
     while (cur.valid) {
@@ -121,9 +108,8 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(const __grid_consta
         unsigned lslot = rpipe.wslot;
         unsigned dslot = 0;
         float vh = 0.f, vl = 0.f, dh = 0.f, dl = 0.f;
-        // cell (i, j), j = s - t + 1, sits on padded diagonal 32k + 2 + s
-        float* qdp = p.Qd + (long long)cur.pair * p.ql.pair_stride + (long long)(k * kTile + 2) * dstep +
-                     (k + 1) * kTile + t;
+        // cell (i, j), j = s - t + 1, is wavefront step sigma = s of strip k
+        float* qdp = p.Qd + (long long)cur.pair * p.ql.pair_stride + (long long)k * p.ql.strip_stride + t;
 
         for (int s = 0; s <= m + 30; ++s) {
             if ((s & 31) == 0 && (s >> 5) < T) {
@@ -188,8 +174,8 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(const __grid_consta
                     nl = t1 - (nh - dh);
                 }
                 qdp[0] = qdx;
-                qdp[Lp] = qdm;
-                qdp[2 * Lp] = qdy;
+                qdp[32] = qdm;
+                qdp[64] = qdy;
             }
             if (t == 31 && feeds_down && in) {
                 bnd_w[j - 1] = make_float2(nh, nl);
@@ -202,7 +188,7 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(const __grid_consta
             dl = ul;
             vh = nh;
             vl = nl;
-            qdp += dstep;
+            qdp += kStepFloats;
         }
         rpipe.next_strip(T);
         qpipe.next_strip(Ta);
@@ -214,8 +200,8 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(const __grid_consta
 // ---------------------------------------------------------------------------
 struct AdjBwdParams {
     const float* E;        // [B, N+2, M+2]
-    const float* Q;        // diagonal-major
-    const float* Qd;       // diagonal-major
+    const float* Q;        // strip-major
+    const float* Qd;       // strip-major
     float* Ed;             // [B, N+2, M+2]
     PairDims d;
     QLayout ql;
@@ -235,9 +221,7 @@ __host__ __device__ inline size_t adj_bwd_smem_bytes(int W, int M) {
 }
 
 template <bool kTMA>
-__global__ void __launch_bounds__(256) softdp_adj_bwd_kernel(const __grid_constant__ CUtensorMap tm_Q,
-                                                             const __grid_constant__ CUtensorMap tm_Qd,
-                                                             AdjBwdParams p) {
+__global__ void __launch_bounds__(256) softdp_adj_bwd_kernel(AdjBwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int W = blockDim.x >> 5, w = threadIdx.x >> 5, t = threadIdx.x & 31;
     const int NB = W + 1;
@@ -264,10 +248,6 @@ __global__ void __launch_bounds__(256) softdp_adj_bwd_kernel(const __grid_consta
     if ((int)threadIdx.x < NB) prog[threadIdx.x] = ~0ull;
     fence_mbar_init();
     __syncthreads();
-    if (kTMA && threadIdx.x == 0) {
-        tma_prefetch_desc(&tm_Q);
-        tma_prefetch_desc(&tm_Qd);
-    }
 
     const bool varlen = (p.d.xlen != nullptr) || (p.d.ylen != nullptr);
     const int u = 31 - t;
@@ -304,20 +284,11 @@ __global__ void __launch_bounds__(256) softdp_adj_bwd_kernel(const __grid_consta
     };
     auto issue_q = [&](const Strip& st, int a, unsigned slot) {
         const int kb = st.K - 1 - st.k;
-        const int dlo = kb * kTile + st.m + 17 - kDiagRows * a;
+        const long long so = (long long)st.pair * p.ql.pair_stride + (long long)kb * p.ql.strip_stride;
         float* dq = qring + (2 * slot) * kDiagElems;
-        float* dqd = dq + kDiagElems;
-        if (kTMA) {
-            if (t == 0) {
-                mbar_expect_tx(&qbars[slot], 2 * kDiagElems * 4);
-                tma_load_4d(dq, &tm_Q, &qbars[slot], (kb + 1) * kTile, 0, dlo, st.pair);
-                tma_load_4d(dqd, &tm_Qd, &qbars[slot], (kb + 1) * kTile, 0, dlo, st.pair);
-            }
-        } else {
-            diag_tile_load_generic(dq, p.Q, p.ql, st.pair, (kb + 1) * kTile, dlo, t);
-            diag_tile_load_generic(dqd, p.Qd, p.ql, st.pair, (kb + 1) * kTile, dlo, t);
-            cp_async_mbar_arrive_noinc(&qbars[slot]);
-        }
+        q_tile_load<kTMA>(dq, &qbars[slot], p.Q + so, st.m + 15 - kDiagRows * a, t, 2);
+        q_tile_load<kTMA>(dq + kDiagElems, &qbars[slot], p.Qd + so, st.m + 15 - kDiagRows * a, t, 0);
+        if (!kTMA) cp_async_mbar_arrive_noinc(&qbars[slot]);
     };
 
     while (cur.valid) {

@@ -85,40 +85,16 @@ bool encode_row_map(CUtensorMap* map, const float* ptr, int B, int N, int M, int
     cuuint32_t box[3] = {(cuuint32_t)boxdim, (cuuint32_t)boxdim, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
-
-// rank-4 map over anti-diagonal-major Q storage [B][ND][3][Lp], box 32 x 3 x kDiagRows x 1
-bool encode_q_map(CUtensorMap* map, const float* ptr, int B, const QLayout& ql) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return false;
-    cuuint64_t dims[4] = {(cuuint64_t)ql.Lp, 3, (cuuint64_t)ql.ND, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)ql.Lp * 4, (cuuint64_t)ql.Lp * 12, (cuuint64_t)ql.pair_stride * 4};
-    cuuint32_t box[4] = {32, 3, kDiagRows, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS;
-}
-
-// Row pitch of the anti-diagonal-major layout: at least N + 33 floats, a multiple of 32;
-// taken from a small fixed set where possible so the fast kernels can be instantiated
-// with the pitch as a compile-time constant.
-constexpr int kLpSet[] = {128, 320, 576, 1088, 2112};
 
 QLayout q_layout(int N, int M) {
     QLayout ql;
-    ql.Lp = ((N + 33 + 31) / 32) * 32;
-    for (int lp : kLpSet)
-        if (lp >= N + 33) {
-            ql.Lp = lp;
-            break;
-        }
-    ql.ND = N + M + 3;
-    ql.pair_stride = (long long)ql.ND * 3 * ql.Lp;
+    ql.K = (N + kTile - 1) / kTile;
+    ql.strip_stride = (long long)(M + 31) * kStepFloats;
+    ql.pair_stride = ql.K * ql.strip_stride;
     return ql;
 }
 
@@ -212,13 +188,13 @@ int b200dp_version(void) { return 100; }
 
 const char* b200dp_last_error(void) { return g_err.c_str(); }
 
-int b200dp_q_layout(int N, int M, int* Lp, int* ND, long long* pair_stride, int* view_offset) {
+int b200dp_q_layout(int N, int M, int* K, long long* strip_stride, long long* pair_stride, long long* pad) {
     if (N < 1 || M < 1) return fail(-1, "b200dp_q_layout: need N >= 1, M >= 1");
     QLayout ql = q_layout(N, M);
-    if (Lp) *Lp = ql.Lp;
-    if (ND) *ND = ql.ND;
+    if (K) *K = ql.K;
+    if (strip_stride) *strip_stride = ql.strip_stride;
     if (pair_stride) *pair_stride = ql.pair_stride;
-    if (view_offset) *view_offset = 31;
+    if (pad) *pad = (long long)kDiagRows * kStepFloats;   // tile reads may run past the last strip
     return 0;
 }
 
@@ -228,7 +204,7 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
     if (mode != B200DP_MODE_NW && mode != B200DP_MODE_SW) return fail(-1, "b200dp_fwd: bad mode");
     if (B == 0) return 0;
     if (!theta || !A || !Q || !Vt) return fail(-1, "b200dp_fwd: null pointer");
-    if (!aligned(Q, 128)) return fail(-1, "b200dp_fwd: Q storage must be 128-byte aligned");
+    if (!aligned(Q, 16)) return fail(-1, "b200dp_fwd: Q storage must be 16-byte aligned");
     Geometry g;
     if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd_smem_bytes, g)) return rc;
     FwdParams p;
@@ -250,21 +226,13 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
     if (fast && encode_row_map(&tmT, theta, B, N, M, kG) && encode_row_map(&tmA, A, B, N, M, kG)) {
         Geometry g2;
         if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes, g2)) return rc;
-        int rc2 = 0;
-        auto launch = [&](auto kern) {
-            rc2 = set_smem(kern, g2.smem, "b200dp_fwd");
-            if (!rc2) kern<<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmT, tmA, p);
-        };
-        const bool sw = mode == B200DP_MODE_SW;
-        switch (p.ql.Lp) {
-            case 128: sw ? launch(softdp_fwd2_kernel<true, 128>) : launch(softdp_fwd2_kernel<false, 128>); break;
-            case 320: sw ? launch(softdp_fwd2_kernel<true, 320>) : launch(softdp_fwd2_kernel<false, 320>); break;
-            case 576: sw ? launch(softdp_fwd2_kernel<true, 576>) : launch(softdp_fwd2_kernel<false, 576>); break;
-            case 1088: sw ? launch(softdp_fwd2_kernel<true, 1088>) : launch(softdp_fwd2_kernel<false, 1088>); break;
-            case 2112: sw ? launch(softdp_fwd2_kernel<true, 2112>) : launch(softdp_fwd2_kernel<false, 2112>); break;
-            default: sw ? launch(softdp_fwd2_kernel<true, 0>) : launch(softdp_fwd2_kernel<false, 0>); break;
+        if (mode == B200DP_MODE_SW) {
+            if (int rc = set_smem(softdp_fwd2_kernel<true>, g2.smem, "b200dp_fwd")) return rc;
+            softdp_fwd2_kernel<true><<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmT, tmA, p);
+        } else {
+            if (int rc = set_smem(softdp_fwd2_kernel<false>, g2.smem, "b200dp_fwd")) return rc;
+            softdp_fwd2_kernel<false><<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmT, tmA, p);
         }
-        if (rc2) return rc2;
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) return cuda_fail(e2, "b200dp_fwd launch");
         return 0;
@@ -288,9 +256,7 @@ int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E, c
     if (mode != B200DP_MODE_NW && mode != B200DP_MODE_SW) return fail(-1, "b200dp_bwd: bad mode");
     if (B == 0) return 0;
     if (!Et || !Q || !E) return fail(-1, "b200dp_bwd: null pointer");
-    if (!aligned(Q, 128)) return fail(-1, "b200dp_bwd: Q storage must be 128-byte aligned");
-    Geometry g;
-    if (int rc = pick_geometry("b200dp_bwd", B, N, M, flags, bwd_smem_bytes, g)) return rc;
+    if (!aligned(Q, 16)) return fail(-1, "b200dp_bwd: Q storage must be 16-byte aligned");
     BwdParams p;
     p.Et = Et;
     p.et_stride = et_stride;
@@ -301,30 +267,26 @@ int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E, c
     p.i0 = mode == B200DP_MODE_SW ? 2 : 1;
     p.flags = flags;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CUtensorMap tmQ;
-    memset(&tmQ, 0, sizeof(tmQ));
-    bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma();
-    if (tma) tma = encode_q_map(&tmQ, Q, B, p.ql);
+    const bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma();
+    Geometry g;
     if (tma && !(flags & B200DP_V1_KERNELS) && !env_v1() && M >= 2 * kG) {
-        Geometry g2;
-        if (int rc = pick_geometry("b200dp_bwd", B, N, M, flags, bwd2_smem_bytes, g2)) return rc;
+        if (int rc = pick_geometry("b200dp_bwd", B, N, M, flags, bwd2_smem_bytes, g)) return rc;
         if (mode == B200DP_MODE_SW) {
-            if (int rc = set_smem(softdp_bwd2_kernel<true>, g2.smem, "b200dp_bwd")) return rc;
-            softdp_bwd2_kernel<true><<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmQ, p);
+            if (int rc = set_smem(softdp_bwd2_kernel<true>, g.smem, "b200dp_bwd")) return rc;
+            softdp_bwd2_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(p);
         } else {
-            if (int rc = set_smem(softdp_bwd2_kernel<false>, g2.smem, "b200dp_bwd")) return rc;
-            softdp_bwd2_kernel<false><<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmQ, p);
+            if (int rc = set_smem(softdp_bwd2_kernel<false>, g.smem, "b200dp_bwd")) return rc;
+            softdp_bwd2_kernel<false><<<g.grid, 32 * g.W, g.smem, st>>>(p);
         }
-        cudaError_t e2 = cudaGetLastError();
-        if (e2 != cudaSuccess) return cuda_fail(e2, "b200dp_bwd launch");
-        return 0;
-    }
-    if (tma) {
-        if (int rc = set_smem(softdp_bwd_kernel<true>, g.smem, "b200dp_bwd")) return rc;
-        softdp_bwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, p);
     } else {
-        if (int rc = set_smem(softdp_bwd_kernel<false>, g.smem, "b200dp_bwd")) return rc;
-        softdp_bwd_kernel<false><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, p);
+        if (int rc = pick_geometry("b200dp_bwd", B, N, M, flags, bwd_smem_bytes, g)) return rc;
+        if (tma) {
+            if (int rc = set_smem(softdp_bwd_kernel<true>, g.smem, "b200dp_bwd")) return rc;
+            softdp_bwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(p);
+        } else {
+            if (int rc = set_smem(softdp_bwd_kernel<false>, g.smem, "b200dp_bwd")) return rc;
+            softdp_bwd_kernel<false><<<g.grid, 32 * g.W, g.smem, st>>>(p);
+        }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "b200dp_bwd launch");
@@ -336,8 +298,8 @@ int b200dp_adj_fwd(const float* Q, const float* Ztheta, const float* ZA, float* 
     if (int rc = check_common("b200dp_adj_fwd", B, N, M)) return rc;
     if (B == 0) return 0;
     if (!Q || !Ztheta || !ZA || !Vtd || !Qd) return fail(-1, "b200dp_adj_fwd: null pointer");
-    if (!aligned(Q, 128) || !aligned(Qd, 128))
-        return fail(-1, "b200dp_adj_fwd: Q/Qd storage must be 128-byte aligned");
+    if (!aligned(Q, 16) || !aligned(Qd, 16))
+        return fail(-1, "b200dp_adj_fwd: Q/Qd storage must be 16-byte aligned");
     Geometry g;
     if (int rc = pick_geometry("b200dp_adj_fwd", B, N, M, flags, adj_fwd_smem_bytes, g)) return rc;
     AdjFwdParams p;
@@ -349,16 +311,12 @@ int b200dp_adj_fwd(const float* Q, const float* Ztheta, const float* ZA, float* 
     p.d = PairDims{xlen, ylen, B, N, M};
     p.ql = q_layout(N, M);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CUtensorMap tmQ;
-    memset(&tmQ, 0, sizeof(tmQ));
-    bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma();
-    if (tma) tma = encode_q_map(&tmQ, Q, B, p.ql);
-    if (tma) {
+    if (!(flags & B200DP_NO_TMA) && !env_no_tma()) {
         if (int rc = set_smem(softdp_adj_fwd_kernel<true>, g.smem, "b200dp_adj_fwd")) return rc;
-        softdp_adj_fwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, p);
+        softdp_adj_fwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(p);
     } else {
         if (int rc = set_smem(softdp_adj_fwd_kernel<false>, g.smem, "b200dp_adj_fwd")) return rc;
-        softdp_adj_fwd_kernel<false><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, p);
+        softdp_adj_fwd_kernel<false><<<g.grid, 32 * g.W, g.smem, st>>>(p);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "b200dp_adj_fwd launch");
@@ -370,8 +328,8 @@ int b200dp_adj_bwd(const float* E, const float* Q, const float* Qd, float* Ed, c
     if (int rc = check_common("b200dp_adj_bwd", B, N, M)) return rc;
     if (B == 0) return 0;
     if (!E || !Q || !Qd || !Ed) return fail(-1, "b200dp_adj_bwd: null pointer");
-    if (!aligned(Q, 128) || !aligned(Qd, 128))
-        return fail(-1, "b200dp_adj_bwd: Q/Qd storage must be 128-byte aligned");
+    if (!aligned(Q, 16) || !aligned(Qd, 16))
+        return fail(-1, "b200dp_adj_bwd: Q/Qd storage must be 16-byte aligned");
     Geometry g;
     if (int rc = pick_geometry("b200dp_adj_bwd", B, N, M, flags, adj_bwd_smem_bytes, g)) return rc;
     AdjBwdParams p;
@@ -382,17 +340,12 @@ int b200dp_adj_bwd(const float* E, const float* Q, const float* Qd, float* Ed, c
     p.d = PairDims{xlen, ylen, B, N, M};
     p.ql = q_layout(N, M);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    CUtensorMap tmQ, tmQd;
-    memset(&tmQ, 0, sizeof(tmQ));
-    memset(&tmQd, 0, sizeof(tmQd));
-    bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma();
-    if (tma) tma = encode_q_map(&tmQ, Q, B, p.ql) && encode_q_map(&tmQd, Qd, B, p.ql);
-    if (tma) {
+    if (!(flags & B200DP_NO_TMA) && !env_no_tma()) {
         if (int rc = set_smem(softdp_adj_bwd_kernel<true>, g.smem, "b200dp_adj_bwd")) return rc;
-        softdp_adj_bwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, tmQd, p);
+        softdp_adj_bwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(p);
     } else {
         if (int rc = set_smem(softdp_adj_bwd_kernel<false>, g.smem, "b200dp_adj_bwd")) return rc;
-        softdp_adj_bwd_kernel<false><<<g.grid, 32 * g.W, g.smem, st>>>(tmQ, tmQd, p);
+        softdp_adj_bwd_kernel<false><<<g.grid, 32 * g.W, g.smem, st>>>(p);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "b200dp_adj_bwd launch");

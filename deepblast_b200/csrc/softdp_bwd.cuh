@@ -5,8 +5,9 @@
 // Push form of the reference's pull recurrence: once E[i,j] is known the cell emits
 //   X = Q[i,j,x] E[i,j] -> (i-1, j),  D = Q[i,j,m] E[i,j] -> (i-1, j-1),
 //   Y = Q[i,j,y] E[i,j] -> (i, j-1),
-// so every lane multiplies by ITS OWN Q[i,j,:] (one coalesced 128-byte line per state
-// in the anti-diagonal-major layout, staged by TMA) instead of its successors'.
+// so every lane multiplies by ITS OWN Q[i,j,:] (strip-major: the sweep reads Q back in
+// exactly the reverse of the order the forward wrote it, 6 KB per 1-D bulk TMA copy)
+// instead of its successors'.
 // Lane t owns row 32kb+t+1 and walks right to left, lane 31 leading; the value a
 // lane hands upward is Z = X(this step) + D(previous step), one shuffle per step.
 // E is staged per 32x32 tile in shared memory and drained row-major, coalesced.
@@ -18,7 +19,7 @@ namespace b200dp {
 struct BwdParams {
     const float* Et;      // [B], stride et_stride (0 for an expanded scalar)
     long long et_stride;
-    const float* Q;       // anti-diagonal-major storage base
+    const float* Q;       // strip-major storage base
     float* E;             // [B, N+2, M+2] row-major
     PairDims d;
     QLayout ql;
@@ -39,7 +40,7 @@ __host__ __device__ inline size_t bwd_smem_bytes(int W, int M) {
 }
 
 template <bool kTMA>
-__global__ void __launch_bounds__(256) softdp_bwd_kernel(const __grid_constant__ CUtensorMap tm_Q, BwdParams p) {
+__global__ void __launch_bounds__(256) softdp_bwd_kernel(BwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int W = blockDim.x >> 5, w = threadIdx.x >> 5, t = threadIdx.x & 31;
     const int NB = W + 1;
@@ -62,7 +63,6 @@ __global__ void __launch_bounds__(256) softdp_bwd_kernel(const __grid_constant__
     if ((int)threadIdx.x < NB) prog[threadIdx.x] = ~0ull;
     fence_mbar_init();
     __syncthreads();
-    if (kTMA && threadIdx.x == 0) tma_prefetch_desc(&tm_Q);
 
     const int N = p.d.N, M = p.d.M;
     const bool varlen = (p.d.xlen != nullptr) || (p.d.ylen != nullptr);
@@ -76,21 +76,14 @@ __global__ void __launch_bounds__(256) softdp_bwd_kernel(const __grid_constant__
     TilePipe<kDiagRing, kDiagRing - 1> pipe;
     pipe.reset();
 
-    // tile a of a strip covers steps [16a, 16a+16): padded diagonals dlo .. dlo+15 with
-    // dlo = 32kb + m + 17 - 16a; rows 32(kb+1) .. +31 of the diagonal-major row axis.
+    // tile a of a strip covers sweep steps [16a, 16a+16); sweep step s touches wavefront
+    // step sigma = m + 30 - s, so the tile is sigma in [m+15-16a, m+30-16a], stored with
+    // sigma ascending: sweep step s reads tile row 15 - (s & 15).
     auto issue = [&](const Strip& st, int a, unsigned slot) {
         const int kb = st.K - 1 - st.k;
-        const int dlo = kb * kTile + st.m + 17 - kDiagRows * a;
-        float* dst = qring + slot * kDiagElems;
-        if (kTMA) {
-            if (t == 0) {
-                mbar_expect_tx(&bars[slot], kDiagElems * 4);
-                tma_load_4d(dst, &tm_Q, &bars[slot], (kb + 1) * kTile, 0, dlo, st.pair);
-            }
-        } else {
-            diag_tile_load_generic(dst, p.Q, p.ql, st.pair, (kb + 1) * kTile, dlo, t);
-            cp_async_mbar_arrive_noinc(&bars[slot]);
-        }
+        const float* strip = p.Q + (long long)st.pair * p.ql.pair_stride + (long long)kb * p.ql.strip_stride;
+        q_tile_load<kTMA>(qring + slot * kDiagElems, &bars[slot], strip, st.m + 15 - kDiagRows * a, t);
+        if (!kTMA) cp_async_mbar_arrive_noinc(&bars[slot]);
     };
 
     while (cur.valid) {

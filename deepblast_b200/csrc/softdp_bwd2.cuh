@@ -3,7 +3,7 @@
 //
 // Same push-form wavefront as softdp_bwd.cuh, re-organised like softdp_fwd2.cuh:
 // 16-step blocks, fully unrolled predicate-free "steady" blocks (12 instructions per
-// step: shuffle, 3 LDS of the lane's own Q from the TMA tile, 5 FP ops, 1 STS), the
+// step: shuffle, 3 LDS of the lane's own Q from the bulk-TMA tile, 5 FP ops, 1 STS), the
 // ramps through the predicated "edge" variant.  E is staged in shared memory in
 // STEP-major order (row = step mod 80, pitch 33 floats) so the hot loop stores with
 // immediate offsets and no bank conflicts; complete 32-column tiles are drained
@@ -30,7 +30,7 @@ __host__ __device__ inline size_t bwd2_smem_bytes(int W, int M) {
 }
 
 template <bool SWM>
-__global__ void __launch_bounds__(256) softdp_bwd2_kernel(const __grid_constant__ CUtensorMap tm_Q, BwdParams p) {
+__global__ void __launch_bounds__(256) softdp_bwd2_kernel(BwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int W = blockDim.x >> 5, w = threadIdx.x >> 5, t = threadIdx.x & 31;
     const int NB = W + 1;
@@ -53,7 +53,6 @@ __global__ void __launch_bounds__(256) softdp_bwd2_kernel(const __grid_constant_
     if ((int)threadIdx.x < NB) prog[threadIdx.x] = ~0ull;
     fence_mbar_init();
     __syncthreads();
-    if (threadIdx.x == 0) tma_prefetch_desc(&tm_Q);
 
     const int N = p.d.N, M = p.d.M;
     const bool varlen = (p.d.xlen != nullptr) || (p.d.ylen != nullptr);
@@ -67,15 +66,12 @@ __global__ void __launch_bounds__(256) softdp_bwd2_kernel(const __grid_constant_
     TilePipe<kB2Ring, kB2Ring - 1> pipe;
     pipe.reset();
 
-    // tile a covers steps [16a, 16a+16): padded diagonals dlo .. dlo+15,
-    // dlo = 32kb + m + 17 - 16a; step s of the tile reads diagonal row 15 - (s & 15)
+    // tile a covers sweep steps [16a, 16a+16) = wavefront steps sigma in
+    // [m+15-16a, m+30-16a] of the strip, 6 KB contiguous; sweep step s reads row 15-(s&15)
     auto issue = [&](const Strip& st, int a, unsigned slot) {
-        if (t == 0) {
-            const int kb = st.K - 1 - st.k;
-            const int dlo = kb * kTile + st.m + 17 - kDiagRows * a;
-            mbar_expect_tx(&bars[slot], kDiagElems * 4);
-            tma_load_4d(qring + slot * kDiagElems, &tm_Q, &bars[slot], (kb + 1) * kTile, 0, dlo, st.pair);
-        }
+        const int kb = st.K - 1 - st.k;
+        const float* strip = p.Q + (long long)st.pair * p.ql.pair_stride + (long long)kb * p.ql.strip_stride;
+        q_tile_load<true>(qring + slot * kDiagElems, &bars[slot], strip, st.m + 15 - kDiagRows * a, t);
     };
 
     while (cur.valid) {

@@ -3,13 +3,16 @@
 // Data layout in HBM:
 //   theta, A, ZA : [B, N, M] fp32 row-major (reference layout, deepblast/nw.py:65-117)
 //   E, Ed, Ztheta: [B, N+2, M+2] fp32 row-major (reference layout, nw.py:347)
-//   Q, Qd        : logical [B, N+2, M+2, 3] (nw.py:105) stored ANTI-DIAGONAL-MAJOR:
-//                  elem(b,i,j,s) = b*pair_stride + (i+j)*3*Lp + s*Lp + (i+31),
-//                  Lp = roundup(N+33, 32).  A torch strided view with strides
-//                  (pair_stride, 3Lp+1, 3Lp, Lp) and storage offset 31 presents it
-//                  with the reference's logical shape.  One anti-diagonal of a
-//                  32-row strip is one 128-byte line per state, so the wavefront's
-//                  stores/loads are perfectly coalesced and TMA-tileable.
+//   Q, Qd        : the reference's [B, N+2, M+2, 3] (nw.py:105) stored STRIP-MAJOR in
+//                  the order the wavefront produces it.  Lattice cell (i, j), 1-based,
+//                  belongs to strip k = (i-1)/32, lane t = (i-1)%32 and is touched at
+//                  wavefront step sigma = (j-1) + t of that strip:
+//                    elem(b,i,j,s) = b*pair_stride + k*strip_stride + sigma*96 + s*32 + t
+//                    strip_stride = (M+31)*96, pair_stride = ceil(N/32)*strip_stride.
+//                  One step of a strip is 384 contiguous bytes (3 states x 32 lanes) and
+//                  consecutive steps are contiguous, so the forward streams Q out
+//                  sequentially and the backward streams it back in with 1-D bulk TMA.
+//                  Border cells (zeros, Q[N+1,M+1,:]=1) are implicit, never stored.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -21,8 +24,9 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kTile = 32;            // rows per strip == lanes; row-major tile is 32 x 32
 constexpr int kTileElems = kTile * kTile;
 constexpr int kRowRing = 3;          // theta/A (row-major, skewed read): 2 live tiles + 1 in flight
-constexpr int kDiagRows = 16;        // anti-diagonals per Q tile
-constexpr int kDiagElems = kDiagRows * 3 * 32;
+constexpr int kStepFloats = 96;      // Q floats per wavefront step of a strip: 3 states x 32 lanes
+constexpr int kDiagRows = 16;        // wavefront steps per Q tile
+constexpr int kDiagElems = kDiagRows * kStepFloats;
 constexpr int kDiagRing = 4;         // Q tiles: 1 live + 3 in flight
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -80,6 +84,14 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// 1-D bulk copy global -> shared (size multiple of 16 B, both addresses 16-B aligned)
+__device__ __forceinline__ void tma_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -89,6 +101,9 @@ __device__ __forceinline__ void cp_async4_zfill(void* dst, const void* src, bool
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src),
                  "r"(valid ? 4 : 0)
                  : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -196,9 +211,9 @@ __device__ __forceinline__ int progress_wait(const unsigned long long* word, uns
 }
 
 struct QLayout {
-    long long pair_stride;   // floats
-    int Lp;                  // floats per (diagonal, state) row, multiple of 32
-    int ND;                  // anti-diagonals per pair = N + M + 3
+    long long pair_stride;    // floats per pair  = K * strip_stride
+    long long strip_stride;   // floats per strip = (M + 31) * 96
+    int K;                    // strips per pair  = ceil(N / 32)
 };
 
 }  // namespace b200dp

@@ -17,12 +17,12 @@ namespace b200dp {
 struct FwdParams {
     const float* theta;   // [B,N,M]
     const float* A;       // [B,N,M]
-    float* Q;             // anti-diagonal-major storage base
+    float* Q;             // strip-major storage base
     float* Vt;            // [B]
     PairDims d;
     QLayout ql;
     int i0;               // 1 = Needleman-Wunsch, 2 = "Smith-Waterman" (sw.py:54-55)
-    int flags;            // bit 0: also write Q's row borders i = 0 and i = n+1
+    int flags;
 };
 
 constexpr int kFwdWarpBytes = 2 * kRowRing * kTileElems * 4;   // theta ring + A ring
@@ -68,9 +68,6 @@ __global__ void __launch_bounds__(256) softdp_fwd_kernel(const __grid_constant__
 
     const RowSrc s_theta{p.theta, (long long)p.d.N * p.d.M, p.d.M, p.d.N, p.d.M};
     const RowSrc s_A{p.A, (long long)p.d.N * p.d.M, p.d.M, p.d.N, p.d.M};
-    const int Lp = p.ql.Lp;
-    const long long dstep = 3ll * Lp;
-
     Strip cur, nxt;
     strip_first(cur, p.d, w, W);
     nxt = cur;
@@ -113,12 +110,10 @@ __global__ void __launch_bounds__(256) softdp_fwd_kernel(const __grid_constant__
         unsigned lslot = pipe.wslot;                 // slot of this strip's tile 0
         float vh = 0.f, vl = 0.f;                    // V[i, j-1]   (own previous)
         float dh = 0.f, dl = 0.f;                    // V[i-1, j-1] (previous shuffle)
-        // cell (i, j) with j = s - t sits on padded diagonal 32k + 1 + s, row slot 32(k+1)+t
-        float* qp = p.Q + (long long)cur.pair * p.ql.pair_stride + (long long)(k * kTile + 1) * dstep +
-                    (k + 1) * kTile + t;
-        const bool borders = (p.flags & 1) != 0;
+        // cell (i, j), j = s - t, is wavefront step sigma = s - 1 of strip k
+        float* qp = p.Q + (long long)cur.pair * p.ql.pair_stride + (long long)k * p.ql.strip_stride + t - kStepFloats;
 
-        for (int s = 0; s <= m + 32; ++s) {
+        for (int s = 0; s <= m + 31; ++s) {
             if ((s & 31) == 0) {
                 const int tq = s >> 5;
                 if (tq < T) {
@@ -168,22 +163,10 @@ __global__ void __launch_bounds__(256) softdp_fwd_kernel(const __grid_constant__
                 nh = dh + t1;
                 nl = t1 - (nh - dh);
             }
-            if (row_ok && j >= 0 && j <= m + 1) {
+            if (in) {
                 qp[0] = qx;
-                qp[Lp] = qm;
-                qp[2 * Lp] = qy;
-                if (borders) {
-                    if (i == 1 && j <= m) {          // cell (0, j+1) shares this diagonal
-                        qp[-1] = 0.f;
-                        qp[Lp - 1] = 0.f;
-                        qp[2 * Lp - 1] = 0.f;
-                    }
-                    if (i == n && j >= 1) {          // cell (n+1, j-1)
-                        qp[1] = 0.f;
-                        qp[Lp + 1] = 0.f;
-                        qp[2 * Lp + 1] = 0.f;
-                    }
-                }
+                qp[32] = qm;
+                qp[64] = qy;
             }
             if (t == 31 && feeds_down && in) {
                 bnd_w[j - 1] = make_float2(nh, nl);
@@ -196,21 +179,7 @@ __global__ void __launch_bounds__(256) softdp_fwd_kernel(const __grid_constant__
             dl = ul;
             vh = nh;
             vl = nl;
-            qp += dstep;
-        }
-        if (borders) {
-            float* qb = p.Q + (long long)cur.pair * p.ql.pair_stride + 31;
-            if (k == 0 && t == 0) {                  // cell (0, 0): diagonal 0
-                qb[0] = 0.f;
-                qb[Lp] = 0.f;
-                qb[2 * Lp] = 0.f;
-            }
-            if (i == n) {                            // Q[n+1, m+1, :] = 1 (nw.py:51)
-                float* qc = qb + (long long)(n + m + 2) * dstep + (n + 1);
-                qc[0] = 1.f;
-                qc[Lp] = 1.f;
-                qc[2 * Lp] = 1.f;
-            }
+            qp += kStepFloats;
         }
         pipe.next_strip(T);
         cur = nxt;

@@ -2,8 +2,8 @@
 // sw.py:46-62; replaces deepblast/nw_cuda.py:46-79).
 //
 // Same wavefront as softdp_fwd.cuh (lane t owns row 32k+t+1, one column per step,
-// V carried as an fp32 (hi, lo) pair, Q written anti-diagonal-major, one 128-byte line
-// per state per step) re-organised for instruction count and occupancy:
+// V carried as an fp32 (hi, lo) pair, Q streamed out strip-major, 384 contiguous bytes
+// per step) re-organised for instruction count and occupancy:
 //   * steps run in blocks of 16; blocks in which every lane is inside the lattice are
 //     fully unrolled with no per-lane predicates ("steady"), the ramps use the
 //     predicated variant of the same step ("edge");
@@ -36,7 +36,7 @@ __host__ __device__ inline size_t fwd2_smem_bytes(int W, int M) {
 // zero border cells; SWM adds the sw.py i, j >= 2 rule.  All state by reference.
 template <bool EDGE, bool SWM>
 __device__ __forceinline__ void fwd2_step(float th, float a, float uh, float ul, float& vh, float& vl, float& dh,
-                                          float& dl, float* __restrict__ qp, int Lp, bool store, bool comp) {
+                                          float& dl, float* __restrict__ qp, bool store, bool comp) {
     // u_x - u_m and u_y - u_m (nw.py:56-58) from the (hi, lo) pairs
     const float dx = ((uh - dh) + (ul - dl)) + a;
     const float dy = ((vh - dh) + (vl - dl)) + a;
@@ -61,8 +61,8 @@ __device__ __forceinline__ void fwd2_step(float th, float a, float uh, float ul,
     }
     if (!EDGE || store) {
         qp[0] = qx;
-        qp[Lp] = qm;
-        qp[2 * Lp] = qy;
+        qp[32] = qm;
+        qp[64] = qy;
     }
     dh = uh;
     dl = ul;
@@ -70,10 +70,7 @@ __device__ __forceinline__ void fwd2_step(float th, float a, float uh, float ul,
     vl = nl;
 }
 
-// LP > 0 fixes the Q row pitch at compile time (b200dp_q_layout picks it from a small
-// set), so every Q store of an unrolled block is base + immediate; LP = 0 reads it
-// from the parameters.
-template <bool SWM, int LP>
+template <bool SWM>
 __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant__ CUtensorMap tm_theta,
                                                           const __grid_constant__ CUtensorMap tm_A, FwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -103,9 +100,6 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
         tma_prefetch_desc(&tm_A);
     }
 
-    const int Lp = LP ? LP : p.ql.Lp;
-    const int dstep = 3 * Lp;
-    const bool borders = (p.flags & 1) != 0;
     // lane-constant part of the tile address: group, row, and the -4*tp column skew
     const int lanebase = g * 2048 + tp * 60;
     // 16 zero (hi, lo) pairs: the "row above" of a pair's first strip
@@ -144,7 +138,7 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
         const int T16 = (m + kG - 1) / kG;
         const int NE = T16 + 1;                       // events of this strip
         const int NEn = nxt.valid ? (nxt.m + kG - 1) / kG + 1 : 0;
-        const int NBk = (m + 32 + 15) / 16;           // blocks: steps s' = 0 .. m+31
+        const int NBk = (m + 31 + 15) / 16;           // blocks: steps s' = 0 .. m+30
         const int i = k * kTile + t + 1;
         const bool row_ok = i <= n;
         const bool rowcomp = row_ok && i >= p.i0;
@@ -158,23 +152,9 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
         unsigned long long* prog_w = prog + (q % NB);
 
         float vh = 0.f, vl = 0.f, dh = 0.f, dl = 0.f;
-        // cell (i, j = c+1), c = s' - t, sits on padded diagonal 32k + 2 + s'
-        float* qp = p.Q + (long long)cur.pair * p.ql.pair_stride + (long long)(k * kTile + 1) * dstep +
-                    (k + 1) * kTile + t;
+        // cell (i, j = c+1), c = s' - t, is wavefront step sigma = s' of strip k
+        float* qp = p.Q + (long long)cur.pair * p.ql.pair_stride + (long long)k * p.ql.strip_stride + t;
         float2* bw31 = bnd_w - 31;
-
-        // prologue step s' = -1: lane 0's zero border cell (i, 0)
-        if (t == 0 && row_ok) {
-            qp[0] = 0.f;
-            qp[Lp] = 0.f;
-            qp[2 * Lp] = 0.f;
-            if (borders && i == 1) {                  // cells (0, 0) and (0, 1)
-                qp[-1] = 0.f; qp[Lp - 1] = 0.f; qp[2 * Lp - 1] = 0.f;
-                float* q0 = qp - dstep;
-                q0[-1] = 0.f; q0[Lp - 1] = 0.f; q0[2 * Lp - 1] = 0.f;
-            }
-        }
-        qp += dstep;
 
         int avail = 0;
         unsigned slotA = 0, slotB = 0;
@@ -193,7 +173,7 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
             }
             const float* baseA = reinterpret_cast<const float*>(ring + slotA * kF2SlotBytes + lanebase + 64);
             const float* baseB = reinterpret_cast<const float*>(ring + slotB * kF2SlotBytes + lanebase);
-            const bool steady = full_rows && b >= 2 && s0 + 16 <= m && !(SWM && k == 0) && !borders;
+            const bool steady = full_rows && b >= 2 && s0 + 16 <= m && !(SWM && k == 0);
             if (steady) {
                 const float2* br = has_up ? bnd_r + s0 : zero_row;
                 float2* bw = bw31 + s0;
@@ -209,10 +189,10 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
                     const float* tb = (tp <= ss) ? baseB : baseA;
                     const float th = tb[ss];
                     const float a = tb[ss + 256];
-                    fwd2_step<false, false>(th, a, uh, ul, vh, vl, dh, dl, qp + ss * dstep, Lp, true, true);
+                    fwd2_step<false, false>(th, a, uh, ul, vh, vl, dh, dl, qp + ss * kStepFloats, true, true);
                     if (t == 31 && feeds_down) bw[ss] = make_float2(vh, vl);
                 }
-                qp += 16 * dstep;
+                qp += 16 * kStepFloats;
             } else {
 #pragma unroll 4
                 for (int ss = 0; ss < 16; ++ss) {
@@ -231,37 +211,22 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
                     }
                     const bool in = row_ok && c >= 0 && c < m;
                     const bool comp = in && rowcomp && (c + 1) >= p.i0;
-                    const bool store = row_ok && c >= -1 && c <= m;
                     float th = 0.f, a = 0.f;
                     if (in) {
                         const float* tb = (tp <= ss) ? baseB : baseA;
                         th = tb[ss];
                         a = tb[ss + 256];
                     }
-                    fwd2_step<true, SWM>(th, a, uh, ul, vh, vl, dh, dl, qp, Lp, store, comp);
-                    if (store && borders) {
-                        if (i == 1 && c + 1 <= m) {   // cell (0, c+2) shares this diagonal
-                            qp[-1] = 0.f; qp[Lp - 1] = 0.f; qp[2 * Lp - 1] = 0.f;
-                        }
-                        if (i == n && c >= 0) {       // cell (n+1, c)
-                            qp[1] = 0.f; qp[Lp + 1] = 0.f; qp[2 * Lp + 1] = 0.f;
-                        }
-                    }
+                    fwd2_step<true, SWM>(th, a, uh, ul, vh, vl, dh, dl, qp, in, comp);
                     if (t == 31 && feeds_down && in) bnd_w[c] = make_float2(vh, vl);
                     if (in && i == n && c == m - 1) p.Vt[cur.pair] = vh + vl;
-                    qp += dstep;
+                    qp += kStepFloats;
                 }
             }
             if (W > 1 && feeds_down && t == 31) {
                 const int done = min(max(s0 + 16 - 31, 0), m);
                 if (done > 0) st_release_u64(prog_w, ((unsigned long long)q << 32) | (unsigned)done);
             }
-        }
-        if (borders && i == n) {                      // Q[n+1, m+1, :] = 1 (nw.py:51)
-            float* qc = p.Q + (long long)cur.pair * p.ql.pair_stride + 31 + (long long)(n + m + 2) * dstep + (n + 1);
-            qc[0] = 1.f;
-            qc[Lp] = 1.f;
-            qc[2 * Lp] = 1.f;
         }
         pipe.next_strip(NE);
         cur = nxt;

@@ -76,20 +76,26 @@ __device__ __forceinline__ void row_tile_load_generic(float* dst, const RowSrc& 
     }
 }
 
-// ---- anti-diagonal-major Q tile: [kDiagRows diagonals][3 states][32 rows] -------
-// Generic path for the same box the TMA map describes.
-__device__ __forceinline__ void diag_tile_load_generic(float* dst, const float* q, const QLayout& ql,
-                                                       int pair, int ip0, int dlo, int lane) {
-    const float* pb = q + (long long)pair * ql.pair_stride;
-#pragma unroll 4
-    for (int dd = 0; dd < kDiagRows; ++dd) {
-        const int d = dlo + dd;
-        const bool ok = d >= 0 && d < ql.ND && (ip0 + lane) < ql.Lp;
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            const float* g = ok ? (pb + ((long long)d * 3 + s) * ql.Lp + ip0 + lane) : q;
-            cp_async4_zfill(dst + (dd * 3 + s) * 32 + lane, g, ok);
+// ---- strip-major Q tile: kDiagRows consecutive wavefront steps = 6 KB contiguous -----
+// Loads steps [sig_lo, sig_lo + 16) of a strip into dst[16][3][32]; steps below 0 (the
+// last tile of a right-to-left sweep) are skipped and their slots left untouched.
+// kTMA: lane 0 arms the mbarrier (for expect_copies equal copies) and issues one 1-D bulk copy.  Otherwise every lane
+// issues 16-byte cp.async and the CALLER arrives (cp_async_mbar_arrive_noinc).
+template <bool kTMA>
+__device__ __forceinline__ void q_tile_load(float* dst, uint64_t* bar, const float* strip, int sig_lo, int lane,
+                                            int expect_copies = 1) {
+    const int lo = sig_lo < 0 ? 0 : sig_lo;
+    const int nsteps = kDiagRows - (lo - sig_lo);
+    const float* src = strip + (long long)lo * kStepFloats;
+    float* d = dst + (lo - sig_lo) * kStepFloats;
+    if (kTMA) {
+        if (lane == 0) {
+            // expect_copies same-sized copies complete on this barrier; the first one arms it
+            if (expect_copies > 0) mbar_expect_tx(bar, (uint32_t)(expect_copies * nsteps) * kStepFloats * 4);
+            tma_bulk_load(d, src, (uint32_t)nsteps * kStepFloats * 4, bar);
         }
+    } else {
+        for (int c = lane; c < nsteps * (kStepFloats / 4); c += 32) cp_async16(d + c * 4, src + c * 4);
     }
 }
 

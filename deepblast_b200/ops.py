@@ -2,16 +2,18 @@
 
 One function per private pass of the reference (deepblast/nw.py:65-117, 138-175,
 202-248, 270-312; deepblast/nw_cuda.py:46-165).  torch is used for device memory
-and streams only.  Q / Qd are returned as strided VIEWS with the reference's
-logical shape [B, N+2, M+2, 3] over anti-diagonal-major storage.
+and streams only.  Q / Qd travel between the passes in the engine's STRIP-MAJOR layout
+ as a 5-D strided view Q5[b, k, t, j-1, s] (strip k, lane t, i.e.
+lattice row i = 32k + t + 1); `q_to_reference` / `q_from_reference` convert to and
+from the reference's dense padded [B, N+2, M+2, 3].
 """
 import torch
 
 from . import _lib
 
 MODES = {"nw": 0, "sw": 1, 0: 0, 1: 1}
-Q_ROW_BORDERS = 0x1
 NO_TMA = 0x2
+V1_KERNELS = 0x4
 
 
 def _ptr(t):
@@ -46,36 +48,60 @@ def _lens(xlen, ylen, B, N, M, device):
 
 
 def q_empty(B, N, M, device):
-    """Allocate anti-diagonal-major storage and return (storage, view[B,N+2,M+2,3])."""
-    Lp, ND, ps, off = _lib.q_layout(N, M)
-    storage = torch.empty(max(B, 1) * ps, dtype=torch.float32, device=device)
-    view = storage.as_strided((B, N + 2, M + 2, 3), (ps, 3 * Lp + 1, 3 * Lp, Lp), off)
-    return storage, view
+    """Allocate strip-major storage; returns the 5-D view [B, K, 32, M, 3]."""
+    K, ss, ps, pad = _lib.q_layout(N, M)
+    storage = torch.empty(max(B, 1) * ps + pad, dtype=torch.float32, device=device)
+    return storage.as_strided((B, K, 32, M, 3), (ps, ss, 97, 96, 32), 0)
 
 
-def q_storage_ptr(Q, N, M):
-    """Storage base pointer of a Q view produced by q_empty (validated)."""
-    Lp, ND, ps, off = _lib.q_layout(N, M)
-    B = Q.shape[0]
-    want = (ps, 3 * Lp + 1, 3 * Lp, Lp)
-    if tuple(Q.shape[1:]) != (N + 2, M + 2, 3) or (B > 1 and Q.stride(0) != ps) or \
-            tuple(Q.stride()[1:]) != want[1:] or Q.dtype != torch.float32:
-        raise RuntimeError(
-            "Q must be the anti-diagonal-major view produced by deepblast_b200 "
-            "(use deepblast_b200.ops.q_from_reference to convert a dense reference-layout Q)")
-    return Q.data_ptr() - 4 * off
+def _is_engine_q(Q, N, M):
+    K, ss, ps, pad = _lib.q_layout(N, M)
+    return (Q.dim() == 5 and tuple(Q.shape[1:]) == (K, 32, M, 3) and Q.dtype == torch.float32
+            and tuple(Q.stride()[1:]) == (ss, 97, 96, 32) and (Q.shape[0] <= 1 or Q.stride(0) == ps)
+            and Q.storage_offset() == 0 and Q.is_cuda)
+
+
+def _as_engine_q(Q, N=None, M=None):
+    """Accept the engine's 5-D view or a dense reference-layout [B,N+2,M+2,3] tensor.
+    Returns (Q5, N, M)."""
+    if Q.dim() == 4 and Q.shape[-1] == 3:
+        return q_from_reference(Q), Q.shape[1] - 2, Q.shape[2] - 2
+    if Q.dim() != 5 or N is None:
+        raise RuntimeError("Q must be deepblast_b200's strip-major view (pass N) or a dense "
+                           "[B, N+2, M+2, 3] reference-layout tensor")
+    M = Q.shape[3]
+    if not _is_engine_q(Q, N, M):
+        raise RuntimeError("Q is not a strip-major view produced by deepblast_b200 for this N, M "
+                           "(use deepblast_b200.ops.q_from_reference to convert a dense Q)")
+    return Q, N, M
 
 
 def q_from_reference(Qref):
-    """Convert a dense reference-layout Q [B,N+2,M+2,3] to the engine's layout."""
+    """Dense reference-layout Q [B,N+2,M+2,3] -> engine layout (5-D view)."""
+    if not Qref.is_cuda:
+        raise RuntimeError("Q must be a CUDA tensor")
     B, N2, M2, _ = Qref.shape
-    storage, view = q_empty(B, N2 - 2, M2 - 2, Qref.device)
-    view.copy_(Qref)
-    return view
+    N, M = N2 - 2, M2 - 2
+    Q5 = q_empty(B, N, M, Qref.device)
+    K = Q5.shape[1]
+    rows = torch.zeros((B, K * 32, M, 3), dtype=torch.float32, device=Qref.device)
+    rows[:, :N] = Qref[:, 1:N + 1, 1:M + 1].float()
+    Q5.copy_(rows.view(B, K, 32, M, 3))
+    return Q5
 
 
-def forward_pass(theta, A, mode="nw", xlen=None, ylen=None, row_borders=False, flags=0):
-    """theta, A [B,N,M] -> (Vt [B], Q view [B,N+2,M+2,3]).  nw.py:65-117."""
+def q_to_reference(Q5, N):
+    """Engine layout -> dense reference-layout [B,N+2,M+2,3] with the implicit borders
+    made explicit: zeros, and Q[N+1, M+1, :] = 1 (nw.py:51)."""
+    B, K, _, M, _ = Q5.shape
+    out = torch.zeros((B, N + 2, M + 2, 3), dtype=torch.float32, device=Q5.device)
+    out[:, 1:N + 1, 1:M + 1] = Q5.reshape(B, K * 32, M, 3)[:, :N]
+    out[:, N + 1, M + 1] = 1.0
+    return out
+
+
+def forward_pass(theta, A, mode="nw", xlen=None, ylen=None, flags=0):
+    """theta, A [B,N,M] -> (Vt [B], Q strip-major view).  nw.py:65-117."""
     _check_in("theta", theta)
     _check_in("A", A, theta.shape)
     B, N, M = theta.shape
@@ -83,60 +109,63 @@ def forward_pass(theta, A, mode="nw", xlen=None, ylen=None, row_borders=False, f
     A = A.detach().contiguous()
     xlen, ylen = _lens(xlen, ylen, B, N, M, theta.device)
     with torch.cuda.device(theta.device):
-        storage, Q = q_empty(B, N, M, theta.device)
+        Q = q_empty(B, N, M, theta.device)
         Vt = torch.empty(B, dtype=torch.float32, device=theta.device)
-        fl = flags | (Q_ROW_BORDERS if row_borders else 0)
-        rc = _lib.lib().b200dp_fwd(_ptr(theta), _ptr(A), _ptr(storage), _ptr(Vt), _ptr(xlen), _ptr(ylen),
-                                   B, N, M, MODES[mode], fl, _stream(theta))
+        rc = _lib.lib().b200dp_fwd(_ptr(theta), _ptr(A), _ptr(Q), _ptr(Vt), _ptr(xlen), _ptr(ylen),
+                                   B, N, M, MODES[mode], flags, _stream(theta))
         _lib.check(rc, "b200dp_fwd")
     return Vt, Q
 
 
-def backward_pass(Et, Q, mode="nw", xlen=None, ylen=None, flags=0):
-    """Et [B] (any stride), Q view -> E [B,N+2,M+2].  nw.py:138-175, 347-352."""
-    B, N2, M2, _ = Q.shape
-    N, M = N2 - 2, M2 - 2
+def backward_pass(Et, Q, mode="nw", xlen=None, ylen=None, flags=0, N=None):
+    """Et [B] (any stride), Q (strip-major view + N, or dense reference layout)
+    -> E [B,N+2,M+2].  nw.py:138-175, 347-352."""
+    Q, N, M = _as_engine_q(Q, N)
+    B = Q.shape[0]
     _check_in("Et", Et, (B,))
     Et = Et.detach()
     xlen, ylen = _lens(xlen, ylen, B, N, M, Q.device)
     with torch.cuda.device(Q.device):
         alloc = torch.zeros if xlen is not None else torch.empty
         E = alloc((B, N + 2, M + 2), dtype=torch.float32, device=Q.device)
-        rc = _lib.lib().b200dp_bwd(_ptr(Et), Et.stride(0) if B > 0 else 0, q_storage_ptr(Q, N, M), _ptr(E),
+        rc = _lib.lib().b200dp_bwd(_ptr(Et), Et.stride(0) if B > 0 else 0, _ptr(Q), _ptr(E),
                                    _ptr(xlen), _ptr(ylen), B, N, M, MODES[mode], flags, _stream(Q))
         _lib.check(rc, "b200dp_bwd")
     return E
 
 
 def adjoint_forward_pass(Q, Ztheta, ZA, xlen=None, ylen=None, flags=0):
-    """Q view, Ztheta [B,N+2,M+2], ZA [B,N,M] -> (Vtd [B], Qd view).  nw.py:202-248."""
-    B, N2, M2, _ = Q.shape
+    """Q, Ztheta [B,N+2,M+2], ZA [B,N,M] -> (Vtd [B], Qd strip-major view).  nw.py:202-248."""
+    B, N2, M2 = Ztheta.shape
     N, M = N2 - 2, M2 - 2
+    Q, N, M = _as_engine_q(Q, N)
     _check_in("Ztheta", Ztheta, (B, N2, M2))
     _check_in("ZA", ZA, (B, N, M))
     Ztheta = Ztheta.detach().contiguous()
     ZA = ZA.detach().contiguous()
     xlen, ylen = _lens(xlen, ylen, B, N, M, Q.device)
     with torch.cuda.device(Q.device):
-        qd_storage, Qd = q_empty(B, N, M, Q.device)
+        Qd = q_empty(B, N, M, Q.device)
         Vtd = torch.empty(B, dtype=torch.float32, device=Q.device)
-        rc = _lib.lib().b200dp_adj_fwd(q_storage_ptr(Q, N, M), _ptr(Ztheta), _ptr(ZA), _ptr(Vtd),
-                                       _ptr(qd_storage), _ptr(xlen), _ptr(ylen), B, N, M, flags, _stream(Q))
+        rc = _lib.lib().b200dp_adj_fwd(_ptr(Q), _ptr(Ztheta), _ptr(ZA), _ptr(Vtd), _ptr(Qd),
+                                       _ptr(xlen), _ptr(ylen), B, N, M, flags, _stream(Q))
         _lib.check(rc, "b200dp_adj_fwd")
     return Vtd, Qd
 
 
 def adjoint_backward_pass(E, Q, Qd, xlen=None, ylen=None, flags=0):
-    """E [B,N+2,M+2], Q view, Qd view -> Ed [B,N+2,M+2].  nw.py:270-312."""
-    B, N2, M2, _ = Q.shape
+    """E [B,N+2,M+2], Q, Qd -> Ed [B,N+2,M+2].  nw.py:270-312."""
+    B, N2, M2 = E.shape
     N, M = N2 - 2, M2 - 2
+    Q, _, _ = _as_engine_q(Q, N)
+    Qd, _, _ = _as_engine_q(Qd, N)
     _check_in("E", E, (B, N2, M2))
     E = E.detach().contiguous()
     xlen, ylen = _lens(xlen, ylen, B, N, M, Q.device)
     with torch.cuda.device(Q.device):
         alloc = torch.zeros if xlen is not None else torch.empty
         Ed = alloc((B, N2, M2), dtype=torch.float32, device=Q.device)
-        rc = _lib.lib().b200dp_adj_bwd(_ptr(E), q_storage_ptr(Q, N, M), q_storage_ptr(Qd, N, M), _ptr(Ed),
+        rc = _lib.lib().b200dp_adj_bwd(_ptr(E), _ptr(Q), _ptr(Qd), _ptr(Ed),
                                        _ptr(xlen), _ptr(ylen), B, N, M, flags, _stream(Q))
         _lib.check(rc, "b200dp_adj_bwd")
     return Ed

@@ -15,11 +15,16 @@
  *   theta, A, ZA   [B, N, M]        contiguous row-major
  *   E, Ed, Ztheta  [B, N+2, M+2]    contiguous row-major (padded lattice, nw.py:347)
  *   Vt, Vtd        [B]
- *   Q, Qd          logical [B, N+2, M+2, 3] (nw.py:105), stored anti-diagonal-major:
- *                  element (b,i,j,s) at  b*pair_stride + (i+j)*3*Lp + s*Lp + i + 31
- *                  with Lp, pair_stride from b200dp_q_layout(); the pointer passed
- *                  is the STORAGE base (128-byte aligned).  State order x=0, m=1,
- *                  y=2 (deepblast/constants.py:1).
+ *   Q, Qd          the reference's [B, N+2, M+2, 3] (nw.py:105) stored STRIP-MAJOR, in the
+ *                  order the wavefront produces it: lattice cell (i, j) (1-based), state
+ *                  s lives at
+ *                    b*pair_stride + k*strip_stride + ((j-1) + t)*96 + s*32 + t,
+ *                    k = (i-1)/32, t = (i-1)%32,
+ *                  with strip_stride = (M+31)*96, pair_stride = ceil(N/32)*strip_stride
+ *                  (b200dp_q_layout()).  Border cells are implicit (zeros, and
+ *                  Q[N+1,M+1,:] = 1) and not stored.  The pointer passed is the storage
+ *                  base (16-byte aligned); the allocation must be B*pair_stride + pad
+ *                  floats.  State order x=0, m=1, y=2 (deepblast/constants.py:1).
  *   xlen, ylen     optional int32[B] per-pair lattice sizes (1 <= n <= N,
  *                  1 <= m <= M); NULL = every pair is N x M.  With lengths, each
  *                  pair is computed exactly as the reference computes the slice
@@ -41,7 +46,6 @@ extern "C" {
 #define B200DP_MODE_SW 1
 
 /* flags */
-#define B200DP_Q_ROW_BORDERS 0x1   /* fwd: also write Q[0,:,:], Q[n+1,:,:] (zeros, corner = 1) */
 #define B200DP_NO_TMA        0x2   /* stage tiles with cp.async instead of TMA (debug / unaligned) */
 #define B200DP_V1_KERNELS    0x4   /* use the general kernels even where the fast path applies */
 #define B200DP_WARPS_SHIFT   4     /* bits 4..7: warps per pair (1,2,4,8); 0 = choose automatically */
@@ -53,14 +57,14 @@ extern "C" {
 int b200dp_version(void);
 const char* b200dp_last_error(void);
 
-/* Anti-diagonal-major Q/Qd geometry for an N x M lattice.
- * view_offset (= 31) is the storage offset of logical element (0,0,0,0); the logical
- * strides are (pair_stride, 3*Lp + 1, 3*Lp, Lp). */
-int b200dp_q_layout(int N, int M, int* Lp, int* ND, long long* pair_stride, int* view_offset);
+/* Strip-major Q/Qd geometry for an N x M lattice (all in floats): strips per pair,
+ * floats per strip, floats per pair, and the tail padding the allocation needs.
+ * As a strided view: Q5[b, k, t, j-1, s] with strides (pair_stride, strip_stride, 97, 96, 32). */
+int b200dp_q_layout(int N, int M, int* K, long long* strip_stride, long long* pair_stride,
+                    long long* pad);
 
 /* replaces _forward_pass_kernel, deepblast/nw_cuda.py:46-79 (sw_cuda.py:46-79):
- * theta, A -> Vt, Q.  Q's column borders j = 0, j = m+1 are written (zeros); its
- * row borders only with B200DP_Q_ROW_BORDERS (no pass reads them). */
+ * theta, A -> Vt, Q (lattice cells; the zero borders are implicit). */
 int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt,
                const int32_t* xlen, const int32_t* ylen, int B, int N, int M,
                int mode, int flags, void* stream);
@@ -73,7 +77,7 @@ int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E,
                int mode, int flags, void* stream);
 
 /* replaces _adjoint_forward_pass_kernel, deepblast/nw_cuda.py:105-139:
- * Q, Ztheta (padded), ZA -> Vtd, Qd (interior cells). */
+ * Q, Ztheta (padded), ZA -> Vtd, Qd. */
 int b200dp_adj_fwd(const float* Q, const float* Ztheta, const float* ZA, float* Vtd,
                    float* Qd, const int32_t* xlen, const int32_t* ylen, int B, int N,
                    int M, int flags, void* stream);

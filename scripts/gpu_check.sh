@@ -3,7 +3,7 @@
 # its own `timeout` so a hung kernel cannot hold the box.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-echo "== staged"; timeout 600 python -u scripts/gpu_stage.py v2 2>&1 | tee gpurun_out/stage.log
+echo "== staged"; timeout 600 python -u scripts/gpu_stage.py 2>&1 | tee gpurun_out/stage.log
 echo "== timing"; timeout 300 python -u scripts/gpu_time.py 2>&1 | tee gpurun_out/time_sweep.log
 echo "== pytest parity"; timeout 900 python -u -m pytest tests/test_gpu_parity.py -m gpu -q -x --maxfail=3 > gpurun_out/pytest_parity.log 2>&1; echo "rc=$?"
 tail -15 gpurun_out/pytest_parity.log

@@ -42,7 +42,7 @@ for W, G in configs:
     try:
         Vt, Q = ops.forward_pass(theta, A, "nw", flags=fl)
         f_ms, f_host = timeit(lambda: ops.forward_pass(theta, A, "nw", flags=fl))
-        b_ms, b_host = timeit(lambda: ops.backward_pass(Et, Q, "nw", flags=fl))
+        b_ms, b_host = timeit(lambda: ops.backward_pass(Et, Q, "nw", flags=fl, N=N))
         print("W=%d grid=%-5d fwd %.3f ms (%.0f GB/s, host %.3f ms)  bwd %.3f ms (%.0f GB/s, host %.3f ms)  fwd+bwd %.1f Gcell/s"
               % (W, G, f_ms, cells * 20 / f_ms / 1e6, f_host, b_ms, cells * 16 / b_ms / 1e6, b_host,
                  cells / (f_ms + b_ms) / 1e6), flush=True)

@@ -42,15 +42,19 @@ def ops():
 def test_golden_forward_backward(golden, ops, name, mode):
     g = lambda k: golden[f"{name}/{k}"]
     theta, A, Et = g("theta"), g("A"), g("Et")
-    Vt, Q = ops.forward_pass(cu(theta), cu(A), mode, row_borders=True)
+    N = theta.shape[1]
+    Vt, Q = ops.forward_pass(cu(theta), cu(A), mode)
     np.testing.assert_allclose(Vt.cpu().numpy(), g(f"{mode}/Vt"), rtol=1e-6)
-    # full padded tensor including zero borders and Q[N+1,M+1,:] = 1
-    np.testing.assert_allclose(Q.cpu().numpy(), g(f"{mode}/Q"), rtol=0, atol=ATOL_QE)
-    E = ops.backward_pass(cu(Et), Q, mode)
+    # full padded tensor: the implicit borders are zeros and Q[N+1,M+1,:] = 1
+    np.testing.assert_allclose(ops.q_to_reference(Q, N).cpu().numpy(), g(f"{mode}/Q"), rtol=0, atol=ATOL_QE)
+    E = ops.backward_pass(cu(Et), Q, mode, N=N)
     np.testing.assert_allclose(E.cpu().numpy(), g(f"{mode}/E"), rtol=0, atol=ATOL_QE * 2)
-    # backward from the REFERENCE's Q converted into the engine layout
-    E2 = ops.backward_pass(cu(Et), ops.q_from_reference(cu(g(f"{mode}/Q"))), mode)
+    # backward from the REFERENCE's dense Q (converted into the engine layout)
+    E2 = ops.backward_pass(cu(Et), cu(g(f"{mode}/Q")), mode)
     np.testing.assert_allclose(E2.cpu().numpy(), g(f"{mode}/E"), rtol=0, atol=2e-6)
+    # layout round trip
+    back = ops.q_to_reference(ops.q_from_reference(cu(g(f"{mode}/Q"))), N).cpu().numpy()
+    np.testing.assert_array_equal(back, g(f"{mode}/Q"))
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -58,12 +62,14 @@ def test_golden_forward_backward(golden, ops, name, mode):
 def test_golden_adjoint(golden, ops, name, mode):
     g = lambda k: golden[f"{name}/{k}"]
     Qref, Eref, Zt, ZA = g(f"{mode}/Q"), g(f"{mode}/E"), g("Zt"), g("ZA")
+    N = Zt.shape[1] - 2
     Q = ops.q_from_reference(cu(Qref))
     Vtd, Qd = ops.adjoint_forward_pass(Q, cu(Zt), cu(ZA))
     scale = max(1.0, float(np.abs(g(f"{mode}/Vtd")).max()))
     np.testing.assert_allclose(Vtd.cpu().numpy(), g(f"{mode}/Vtd"), rtol=0, atol=1e-5 * scale)
-    np.testing.assert_allclose(interior(Qd).cpu().numpy(), interior(g(f"{mode}/Qd")), rtol=0, atol=1e-5 * scale)
-    Ed = ops.adjoint_backward_pass(cu(Eref), Q, ops.q_from_reference(cu(g(f"{mode}/Qd"))))
+    np.testing.assert_allclose(interior(ops.q_to_reference(Qd, N)).cpu().numpy(), interior(g(f"{mode}/Qd")),
+                               rtol=0, atol=1e-5 * scale)
+    Ed = ops.adjoint_backward_pass(cu(Eref), Q, cu(g(f"{mode}/Qd")))
     np.testing.assert_allclose(Ed.cpu().numpy(), g(f"{mode}/Ed"), rtol=0, atol=1e-5 * scale)
     # chained on the engine's own Qd
     Ed2 = ops.adjoint_backward_pass(cu(Eref), Q, Qd)
@@ -82,21 +88,16 @@ SHAPES = [(2, 1, 1), (2, 1, 9), (2, 9, 1), (3, 31, 33), (2, 32, 32), (2, 64, 64)
 
 
 def check_fwd_bwd(ops, theta, A, Et, mode, flags):
-    """Forward + backward against the oracle, with and without Q's row borders (the
-    fast kernels only run their unrolled blocks without them)."""
+    """Forward + backward against the oracle."""
+    N = theta.shape[1]
     Vt_o, Q_o = O.forward_pass(theta.numpy(), A.numpy(), mode)
     E_o = O.backward_pass(Et.numpy(), Q_o, mode)
     th, a = theta.to(dev()), A.to(dev())
-    Vt, Q = ops.forward_pass(th, a, mode, row_borders=True, flags=flags)
+    Vt, Q = ops.forward_pass(th, a, mode, flags=flags)
     np.testing.assert_allclose(Vt.cpu().numpy(), Vt_o, rtol=1e-6)
-    np.testing.assert_allclose(Q.cpu().numpy(), Q_o, rtol=0, atol=ATOL_QE)
-    Vt2, Q2 = ops.forward_pass(th, a, mode, row_borders=False, flags=flags)
-    np.testing.assert_allclose(Vt2.cpu().numpy(), Vt_o, rtol=1e-6)
-    # rows 1..N with their zero column borders j = 0 and j = M+1
-    np.testing.assert_allclose(Q2[:, 1:-1].cpu().numpy(), Q_o[:, 1:-1], rtol=0, atol=ATOL_QE)
-    for q in (Q, Q2):
-        E = ops.backward_pass(Et.to(dev()), q, mode, flags=flags)
-        np.testing.assert_allclose(E.cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
+    np.testing.assert_allclose(ops.q_to_reference(Q, N).cpu().numpy(), Q_o, rtol=0, atol=ATOL_QE)
+    E = ops.backward_pass(Et.to(dev()), Q, mode, flags=flags, N=N)
+    np.testing.assert_allclose(E.cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
 
 
 @pytest.mark.parametrize("B,N,M", SHAPES)
@@ -118,9 +119,9 @@ def test_warps_per_pair(ops, W, mode, kern):
     E_o = O.backward_pass(np.ones(B, np.float32), Q_o, mode)
     fl = (W << 4) | kern
     Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), mode, flags=fl)
-    E = ops.backward_pass(torch.ones(B, device=dev()), Q, mode, flags=fl)
+    E = ops.backward_pass(torch.ones(B, device=dev()), Q, mode, flags=fl, N=N)
     np.testing.assert_allclose(Vt.cpu().numpy(), Vt_o, rtol=1e-6)
-    np.testing.assert_allclose(interior(Q).cpu().numpy(), interior(Q_o), rtol=0, atol=ATOL_QE)
+    np.testing.assert_allclose(ops.q_to_reference(Q, N).cpu().numpy(), Q_o, rtol=0, atol=ATOL_QE)
     np.testing.assert_allclose(E.cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
     g = torch.Generator().manual_seed(9)
     Zt = torch.randn(B, N + 2, M + 2, generator=g)
@@ -143,7 +144,7 @@ def test_persistent_grid_many_pairs_per_cta(ops):
     for W, kern in ((1, 0), (2, 0), (1, V1), (2, V1)):
         fl = (W << 4) | (3 << 8) | kern   # 3 CTAs for 13 pairs
         Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), "nw", flags=fl)
-        E = ops.backward_pass(torch.ones(B, device=dev()), Q, "nw", flags=fl)
+        E = ops.backward_pass(torch.ones(B, device=dev()), Q, "nw", flags=fl, N=N)
         np.testing.assert_allclose(Vt.cpu().numpy(), Vt_o, rtol=1e-6)
         np.testing.assert_allclose(E.cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
 
@@ -157,7 +158,7 @@ def test_ragged_lengths_match_per_pair_oracle(ops):
     ylen = torch.tensor([120, 120, 1, 32, 65, 7], dtype=torch.int32)
     for mode in ("nw", "sw"):
         Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), mode, xlen, ylen)
-        E = ops.backward_pass(torch.ones(B, device=dev()), Q, mode, xlen, ylen)
+        E = ops.backward_pass(torch.ones(B, device=dev()), Q, mode, xlen, ylen, N=N)
         Vt, E = Vt.cpu().numpy(), E.cpu().numpy()
         for b in range(B):
             n, m = int(xlen[b]), int(ylen[b])
@@ -179,14 +180,14 @@ def test_full_size_properties(ops, mode):
     th, a = theta.to(dev()), A.to(dev())
     Vt, Q = ops.forward_pass(th, a, mode)
     Et = torch.ones(B, device=dev())
-    E = ops.backward_pass(Et, Q, mode)
-    Qi = interior(Q)
+    E = ops.backward_pass(Et, Q, mode, N=N)
+    Qi = interior(ops.q_to_reference(Q, N))
     lo = 1 if mode == "sw" else 0
     s = Qi[:, lo:, lo:].sum(-1)
     assert torch.allclose(s, torch.ones_like(s), atol=1e-5)            # softmax rows sum to 1
     assert (Qi >= 0).all() and torch.isfinite(Vt).all()
     # E is linear in Et (nw.py:125)
-    E3 = ops.backward_pass(Et * 3.0, Q, mode)
+    E3 = ops.backward_pass(Et * 3.0, Q, mode, N=N)
     assert torch.allclose(E3[:, 1:-1, 1:-1], 3.0 * E[:, 1:-1, 1:-1], rtol=1e-5, atol=1e-6)
     # expected alignment: E[N,M] = Et; every anti-diagonal band carries total flow <= Et
     assert torch.allclose(E[:, N, M], Et)
@@ -199,7 +200,7 @@ def test_full_size_properties(ops, mode):
     Vt_o, Q_o = O.forward_pass(theta[idx].numpy(), A[idx].numpy(), mode)
     E_o = O.backward_pass(np.ones(3, np.float32), Q_o, mode)
     np.testing.assert_allclose(Vt[idx].cpu().numpy(), Vt_o, rtol=1e-6)
-    np.testing.assert_allclose(interior(Q[idx]).cpu().numpy(), interior(Q_o), rtol=0, atol=ATOL_QE)
+    np.testing.assert_allclose(Qi[idx].cpu().numpy(), interior(Q_o), rtol=0, atol=ATOL_QE)
     np.testing.assert_allclose(E[idx].cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
 
 
@@ -210,9 +211,9 @@ def test_large_lattice_1024(ops):
     Vt_o, Q_o = O.forward_pass(theta.numpy(), A.numpy(), "nw")
     E_o = O.backward_pass(np.ones(1, np.float32), Q_o, "nw")
     Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), "nw")
-    E = ops.backward_pass(torch.ones(1, device=dev()), Q, "nw")
+    E = ops.backward_pass(torch.ones(1, device=dev()), Q, "nw", N=N)
     np.testing.assert_allclose(Vt.cpu().numpy(), Vt_o, rtol=1e-6)
-    np.testing.assert_allclose(interior(Q).cpu().numpy(), interior(Q_o), rtol=0, atol=ATOL_QE)
+    np.testing.assert_allclose(ops.q_to_reference(Q, N).cpu().numpy(), Q_o, rtol=0, atol=ATOL_QE)
     np.testing.assert_allclose(E.cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
 
 
@@ -263,7 +264,7 @@ def test_end_to_end_traceback_agreement(ops):
     B, N, M = 4, 256, 193
     theta, A = rand_inputs(B, N, M, seed=2)
     Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), "nw")
-    E = ops.backward_pass(torch.ones(B, device=dev()), Q, "nw")
+    E = ops.backward_pass(torch.ones(B, device=dev()), Q, "nw", N=N)
     got = ops.traceback_batch(E[:, 1:-1, 1:-1], variant="cuda")
     _, _, E_o = O.decode(theta.numpy(), A.numpy(), "nw")
     for b in range(B):

@@ -29,16 +29,16 @@ def test_library_exports_header_symbols():
 def test_q_layout_is_a_valid_strided_view():
     from deepblast_b200 import _lib
     for N, M in [(1, 1), (5, 4), (31, 33), (32, 32), (256, 256), (300, 77), (1000, 2047)]:
-        Lp, ND, ps, off = _lib.q_layout(N, M)
-        assert Lp % 32 == 0 and Lp >= N + 33 and ND == N + M + 3 and ps == ND * 3 * Lp and off == 31
-        # the logical strides address distinct elements inside the pair's storage
-        i, j, s = np.meshgrid(np.arange(N + 2), np.arange(M + 2), np.arange(3), indexing="ij")
-        addr = off + i * (3 * Lp + 1) + j * (3 * Lp) + s * Lp
-        assert addr.min() >= 0 and addr.max() < ps
-        if (N + 2) * (M + 2) <= 40000:
+        K, ss, ps, pad = _lib.q_layout(N, M)
+        assert K == (N + 31) // 32 and ss == (M + 31) * 96 and ps == K * ss and pad >= 16 * 96
+        # the 5-D view [K, 32, M, 3] with strides (ss, 97, 96, 32) addresses distinct
+        # elements inside the pair's storage: cell (i, j, s) -> k*ss + ((j-1)+t)*96 + s*32 + t
+        if K * 32 * M <= 40000:
+            k, t, j0, s = np.meshgrid(np.arange(K), np.arange(32), np.arange(M), np.arange(3), indexing="ij")
+            addr = k * ss + t * 97 + j0 * 96 + s * 32
+            assert addr.min() >= 0 and addr.max() < ps
             assert len(np.unique(addr)) == addr.size
-        # interior rows of strip k start a 128-byte line: (i + 31) % 32 == 0 for i = 32k + 1
-        assert (1 + 31) % 32 == 0
+            np.testing.assert_array_equal(addr, k * ss + (j0 + t) * 96 + s * 32 + t)
 
 
 def test_argument_errors_do_not_need_a_gpu():
