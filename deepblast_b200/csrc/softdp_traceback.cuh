@@ -41,10 +41,15 @@ __global__ void softdp_traceback_kernel(TracebackParams p) {
     len = 1;
     for (;;) {
         float left, diag, upper;
-        left = (i <= 0) ? sentinel : g[(long long)(i - 1) * p.si + (long long)j * p.sj];
+        // every read uses Python index semantics: -n <= idx < n, negatives wrap, anything
+        // else is an IndexError (j can go negative once a diagonal move wrapped column 0)
+        if (i <= 0) left = sentinel;
+        else {
+            if (j < -m || j >= m) { status = -2; break; }
+            left = g[(long long)(i - 1) * p.si + (long long)tb_wrap(j, m) * p.sj];
+        }
         if (i <= 0 && j <= 0) diag = sentinel;
         else {
-            // Python negative indices wrap around (exactly one of i, j can be <= 0 here)
             if (i - 1 < -n || j - 1 < -m) { status = -2; break; }
             diag = g[(long long)tb_wrap(i - 1, n) * p.si + (long long)tb_wrap(j - 1, m) * p.sj];
         }

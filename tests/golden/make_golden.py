@@ -169,6 +169,31 @@ def main():
                 tb = np.array([[-999, -999, -999]], dtype=np.int32)
             out[f"tb_rand{idx}/tb_{variant}"] = tb
     meta["n_tb_rand"] = 6
+    # many small random matrices with ties and zeros: pins the Python index semantics
+    # (negative wrap-around of rows AND columns, IndexError) of both traceback rules
+    rng = np.random.default_rng(11)
+    grads, tbs = [], {"cpu": [], "cuda": []}
+    n_small = 300
+    for idx in range(n_small):
+        N, M = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        gm = np.round(rng.random((N, M)) * 4).astype(np.float32) / 4     # quantised: many exact ties
+        gm[rng.random((N, M)) < 0.35] = 0.0
+        pad = np.full((8, 8), np.nan, dtype=np.float32)
+        pad[:N, :M] = gm
+        grads.append(pad)
+        for variant, dec in (("cpu", rnw.NeedlemanWunschDecoder('softmax')),
+                             ("cuda", rnwc.NeedlemanWunschDecoder('softmax'))):
+            try:
+                tb = np.array(dec.traceback(torch.from_numpy(gm)), dtype=np.int32)
+            except IndexError:
+                tb = np.array([[-999, -999, -999]], dtype=np.int32)
+            row = np.full((40, 3), -12345, dtype=np.int32)
+            row[:len(tb)] = tb
+            tbs[variant].append(row)
+        meta.setdefault("tb_small_shapes", []).append([N, M])
+    out["tb_small/grad"] = np.stack(grads)
+    out["tb_small/tb_cpu"] = np.stack(tbs["cpu"])
+    out["tb_small/tb_cuda"] = np.stack(tbs["cuda"])
 
     np.savez_compressed(os.path.join(HERE, "softdp_golden.npz"), **out)
     with open(os.path.join(HERE, "softdp_golden.json"), "w") as f:

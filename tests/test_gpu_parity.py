@@ -233,6 +233,23 @@ def test_traceback_bit_exact(golden, golden_meta, ops):
                     ops.traceback_batch(grad, variant=variant)
             else:
                 assert ops.traceback_batch(grad, variant=variant)[0] == [tuple(r) for r in want]
+    # 300 tie-rich small matrices traced by the reference (negative-index wrap-around on
+    # rows and columns, IndexError cases), batched with per-pair lengths in ONE launch
+    shapes = golden_meta["tb_small_shapes"]
+    gsm = cu(np.nan_to_num(golden["tb_small/grad"], nan=7.0))
+    xl = torch.tensor([s[0] for s in shapes], dtype=torch.int32)
+    yl = torch.tensor([s[1] for s in shapes], dtype=torch.int32)
+    for variant in ("cpu", "cuda"):
+        want_all = golden[f"tb_small/tb_{variant}"]
+        ok = [i for i in range(len(shapes)) if want_all[i, 0, 0] != -999]
+        bad = [i for i in range(len(shapes)) if want_all[i, 0, 0] == -999]
+        got = ops.traceback_batch(gsm[ok], xl[ok], yl[ok], variant)
+        for i, gi in zip(ok, got):
+            w = want_all[i]
+            assert gi == [tuple(r) for r in w[w[:, 0] != -12345].tolist()], (i, variant)
+        for i in bad[:5]:
+            with pytest.raises(IndexError):
+                ops.traceback_batch(gsm[i:i + 1], xl[i:i + 1], yl[i:i + 1], variant)
     # non-contiguous batched input with ragged lengths == per-pair oracle
     g = torch.Generator().manual_seed(1)
     big = torch.rand(4, 40, 60, generator=g)

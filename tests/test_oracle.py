@@ -83,6 +83,25 @@ def test_traceback_random(golden, golden_meta):
                 assert O.traceback(grad, variant) == [tuple(r) for r in want]
 
 
+def test_traceback_small_matrices(golden, golden_meta):
+    """300 quantised (tie-rich) matrices traced by the reference: Python's negative-index
+    wrap-around on rows AND columns and its IndexError cases, both stop rules."""
+    shapes = golden_meta["tb_small_shapes"]
+    n_err = 0
+    for idx, (N, M) in enumerate(shapes):
+        grad = golden["tb_small/grad"][idx, :N, :M]
+        for variant in ("cpu", "cuda"):
+            want = golden[f"tb_small/tb_{variant}"][idx]
+            want = want[want[:, 0] != -12345]
+            if want.tolist() == [[-999, -999, -999]]:
+                n_err += 1
+                with pytest.raises(IndexError):
+                    O.traceback(grad, variant)
+            else:
+                assert O.traceback(grad, variant) == [tuple(r) for r in want.tolist()], (idx, variant)
+    assert n_err > 10
+
+
 def test_reference_known_answers(golden, golden_meta):
     """The literal expectations of the reference's own unit tests."""
     ka = golden_meta["known_answers"]
