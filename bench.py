@@ -252,6 +252,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     sync_all()
+    host_t0 = time.perf_counter()
     ev0.record()
     for it in range(args.steps):
         kev[it][0].record()
@@ -263,6 +264,7 @@ def main():
         g, = torch.autograd.grad(Vt.sum(), theta)
         kev[it][2].record()
     ev1.record()
+    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps     # enqueue time, GPU not waited for
     torch.cuda.synchronize()
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
@@ -342,6 +344,7 @@ def main():
                          "bwd": {"ms": bwd_ms, "GBps": bwd_gbs, "frac": bwd_gbs / peak},
                          "step": {"GBps_at_36B_per_cell": step_gbs, "frac": step_gbs / peak}},
             "gpu_launches": 2 * args.steps,
+            "host_enqueue_ms_per_step": host_ms,
             "clocks": clocks,
         }
         if e2e:

@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <string>
 
 #include "../../include/b200dp.h"
@@ -162,10 +164,25 @@ int pick_geometry(const char* fn, int B, int N, int M, int flags, SmemFn smem_of
     return 0;
 }
 
+// cudaFuncSetAttribute is not free (and may serialise with work in flight): remember,
+// per device and kernel, the largest dynamic shared-memory size already granted.
 template <class Kern>
 int set_smem(Kern k, size_t smem, const char* fn) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> granted;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::pair<int, const void*> key(dev, reinterpret_cast<const void*>(k));
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = granted.find(key);
+        if (it != granted.end() && it->second >= smem) return 0;
+    }
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, fn);
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& g = granted[key];
+    if (g < smem) g = smem;
     return 0;
 }
 
@@ -226,7 +243,16 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
     if (fast && encode_row_map(&tmT, theta, B, N, M, kG) && encode_row_map(&tmA, A, B, N, M, kG)) {
         Geometry g2;
         if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes, g2)) return rc;
-        if (mode == B200DP_MODE_SW) {
+        int dbg = 0;
+        if (const char* e = getenv("B200DP_DBG")) dbg = atoi(e);     // diagnostics: see softdp_fwd2.cuh
+        if (dbg >= 1 && dbg <= 3) {
+            auto run = [&](auto kern) {
+                if (set_smem(kern, g2.smem, "b200dp_fwd") == 0) kern<<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmT, tmA, p);
+            };
+            if (dbg == 1) run(softdp_fwd2_kernel<false, 1>);
+            else if (dbg == 2) run(softdp_fwd2_kernel<false, 2>);
+            else run(softdp_fwd2_kernel<false, 3>);
+        } else if (mode == B200DP_MODE_SW) {
             if (int rc = set_smem(softdp_fwd2_kernel<true>, g2.smem, "b200dp_fwd")) return rc;
             softdp_fwd2_kernel<true><<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmT, tmA, p);
         } else {

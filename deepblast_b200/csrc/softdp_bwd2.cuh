@@ -26,6 +26,7 @@ __host__ __device__ inline size_t bwd2_smem_bytes(int W, int M) {
     b += (size_t)(W + 1) * 8;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)(W + 1) * (size_t)M * 4;
+    b += 256;                                      // slack for the ramps' clamped boundary reads
     return b;
 }
 
@@ -148,30 +149,28 @@ __global__ void __launch_bounds__(256) softdp_bwd2_kernel(BwdParams p) {
                     if (t == 0 && feeds_up) bw[-ss] = zout;
                 }
             } else {
+                // ramp blocks: the steady step with the lattice-membership selects.  Q in
+                // the ramps is never written by the forward (arbitrary bits), so the
+                // products are selected, not multiplied by zero.
+                const bool seed_blk = (cur.k == 0) && (s0 < 32);   // E[n, m] = Et lives here
 #pragma unroll 4
                 for (int ss = 0; ss < 16; ++ss) {
-                    const int s = s0 + ss;
-                    const int c = m - 1 - (s - u);
+                    const int c = m - 1 - (s0 + ss - u);
                     float zin = __shfl_down_sync(kFull, zout, 1);
-                    if (t == 31) {
-                        zin = 0.f;
-                        if (has_below && c >= 0) zin = bnd_r[c];
-                    }
-                    const bool in = row_ok && c >= 0 && c < m;
-                    const bool comp = in && rowcomp && (c + 1) >= p.i0;
-                    float e = 0.f, X = 0.f, D = 0.f, Y = 0.f;
-                    if (comp) {
-                        e = zin + yprev;
-                        if (i == n && c == m - 1) e = et;     // E[n, m] = Et (nw.py:125-127)
-                        X = qt[(15 - ss) * 96] * e;
-                        D = qt[(15 - ss) * 96 + 32] * e;
-                        Y = qt[(15 - ss) * 96 + 64] * e;
-                    }
+                    if (t == 31) zin = (has_below && c >= 0) ? bnd_r[c] : 0.f;
+                    const bool in = row_ok && (unsigned)c < (unsigned)m;
+                    const bool comp = SWM ? (in && rowcomp && (c + 1) >= 2) : in;
+                    float e = zin + yprev;
+                    if (seed_blk && i == n && c == m - 1) e = et;   // nw.py:125-127
+                    e = comp ? e : 0.f;
+                    const float X = comp ? qt[(15 - ss) * 96] * e : 0.f;
+                    const float D = comp ? qt[(15 - ss) * 96 + 32] * e : 0.f;
+                    const float Y = comp ? qt[(15 - ss) * 96 + 64] * e : 0.f;
                     st[ss * kB2StagePitch] = e;
                     zout = X + dprev;
                     dprev = D;
                     yprev = Y;
-                    if (t == 0 && feeds_up && c >= 0 && c < m) bnd_w[c] = zout;
+                    if (t == 0 && feeds_up && in) bnd_w[c] = zout;
                 }
             }
             if (W > 1 && feeds_up && t == 0) {

@@ -67,6 +67,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One lane of a converged warp, known to the compiler to be exactly one (elect.sync):
+// TMA issue under this predicate needs no per-lane serialisation loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(p));
+    return p != 0;
+}
+
 // ---- TMA (cp.async.bulk.tensor) -------------------------------------------
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
                                             int c2) {

@@ -28,13 +28,14 @@ __host__ __device__ inline size_t fwd2_smem_bytes(int W, int M) {
     b += (size_t)(W + 1) * 8;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)(W + 1) * (size_t)M * 8;
-    b += 128;                                      // 16 zero (hi, lo) pairs
+    b += 512;                                      // 16 zero (hi, lo) pairs + slack for ramp reads
     return b;
 }
 
 // One wavefront step of one lane.  EDGE adds the lattice-membership predicates and the
 // zero border cells; SWM adds the sw.py i, j >= 2 rule.  All state by reference.
-template <bool EDGE, bool SWM>
+// DBG (diagnostic builds only): bit 0 = drop the Q stores, bit 1 = no theta/A staging.
+template <bool EDGE, bool SWM, int DBG = 0>
 __device__ __forceinline__ void fwd2_step(float th, float a, float uh, float ul, float& vh, float& vl, float& dh,
                                           float& dl, float* __restrict__ qp, bool store, bool comp) {
     // u_x - u_m and u_y - u_m (nw.py:56-58) from the (hi, lo) pairs
@@ -54,12 +55,19 @@ __device__ __forceinline__ void fwd2_step(float th, float a, float uh, float ul,
     float nh = dh + t1;
     float nl = t1 - (nh - dh);
     if (EDGE || SWM) {
-        if (!comp) {
-            qx = qm = qy = 0.f;
-            nh = nl = 0.f;
+        // outside the lattice (or below the sw.py origin) V is 0; Q there is only stored
+        // (as zeros) for sw.py's first row / column
+        nh = comp ? nh : 0.f;
+        nl = comp ? nl : 0.f;
+        if (SWM) {
+            qx = comp ? qx : 0.f;
+            qm = comp ? qm : 0.f;
+            qy = comp ? qy : 0.f;
         }
     }
-    if (!EDGE || store) {
+    if (DBG & 1) {
+        if (qx + qm + qy == 12345.f) qp[0] = qx;     // keeps the math alive, never true
+    } else if (!EDGE || store) {
         qp[0] = qx;
         qp[32] = qm;
         qp[64] = qy;
@@ -70,7 +78,7 @@ __device__ __forceinline__ void fwd2_step(float th, float a, float uh, float ul,
     vl = nl;
 }
 
-template <bool SWM>
+template <bool SWM, int DBG = 0>
 __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant__ CUtensorMap tm_theta,
                                                           const __grid_constant__ CUtensorMap tm_A, FwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -117,7 +125,7 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
 
     // event e of a strip = {group 0: tile e, group 1: tile e-1} x {theta, A}
     auto issue = [&](const Strip& st, int e, unsigned slot) {
-        if (t == 0) {
+        if (!(DBG & 2) && elect_one()) {
             const int T16 = (st.m + kG - 1) / kG;
             unsigned char* dst = ring + slot * kF2SlotBytes;
             const bool g0 = e < T16, g1 = e >= 1;
@@ -164,7 +172,12 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
             if (b < NE) {
                 pipe.pump(b, NE, nxt.valid, NEn,
                           [&](bool from_next, int e, unsigned slot) { issue(from_next ? nxt : cur, e, slot); });
-                slotB = pipe.wait(bars);
+                if (DBG & 2) {
+                    slotB = pipe.wslot;
+                    pipe.wslot = (pipe.wslot + 1 == kF2Ring) ? 0u : pipe.wslot + 1;
+                } else {
+                    slotB = pipe.wait(bars);
+                }
             }
             const int s0 = b * 16;
             if (W > 1 && has_up && s0 < m) {
@@ -189,37 +202,33 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
                     const float* tb = (tp <= ss) ? baseB : baseA;
                     const float th = tb[ss];
                     const float a = tb[ss + 256];
-                    fwd2_step<false, false>(th, a, uh, ul, vh, vl, dh, dl, qp + ss * kStepFloats, true, true);
+                    fwd2_step<false, false, DBG>(th, a, uh, ul, vh, vl, dh, dl, qp + ss * kStepFloats, true, true);
                     if (t == 31 && feeds_down) bw[ss] = make_float2(vh, vl);
                 }
                 qp += 16 * kStepFloats;
             } else {
+                // ramp blocks: the steady step with the lattice-membership selects
+                const bool cap = (k + 1 == cur.K) && (((m - 1 + ((n - 1) & 31)) >> 4) == b);
+                const float2* br = has_up ? bnd_r + s0 : zero_row;
+                const int brlim = has_up ? m - s0 : 16;      // entries of br that exist
 #pragma unroll 4
                 for (int ss = 0; ss < 16; ++ss) {
-                    const int sp = s0 + ss;           // s'
-                    const int c = sp - t;
+                    const int c = s0 + ss - t;
                     float uh = __shfl_up_sync(kFull, vh, 1);
                     float ul = __shfl_up_sync(kFull, vl, 1);
                     if (t == 0) {
-                        uh = 0.f;
-                        ul = 0.f;
-                        if (has_up && c < m) {
-                            const float2 bv = bnd_r[c];
-                            uh = bv.x;
-                            ul = bv.y;
-                        }
+                        const float2 bv = br[ss < brlim ? ss : 0];
+                        uh = bv.x;
+                        ul = bv.y;
                     }
-                    const bool in = row_ok && c >= 0 && c < m;
-                    const bool comp = in && rowcomp && (c + 1) >= p.i0;
-                    float th = 0.f, a = 0.f;
-                    if (in) {
-                        const float* tb = (tp <= ss) ? baseB : baseA;
-                        th = tb[ss];
-                        a = tb[ss + 256];
-                    }
-                    fwd2_step<true, SWM>(th, a, uh, ul, vh, vl, dh, dl, qp, in, comp);
+                    const bool in = row_ok && (unsigned)c < (unsigned)m;
+                    const bool comp = SWM ? (in && rowcomp && (c + 1) >= 2) : in;
+                    const float* tb = (tp <= ss) ? baseB : baseA;
+                    const float th = tb[ss];
+                    const float a = tb[ss + 256];
+                    fwd2_step<true, SWM, DBG>(th, a, uh, ul, vh, vl, dh, dl, qp, in, comp);
                     if (t == 31 && feeds_down && in) bnd_w[c] = make_float2(vh, vl);
-                    if (in && i == n && c == m - 1) p.Vt[cur.pair] = vh + vl;
+                    if (cap && in && i == n && c == m - 1) p.Vt[cur.pair] = vh + vl;
                     qp += kStepFloats;
                 }
             }

@@ -89,7 +89,7 @@ __device__ __forceinline__ void q_tile_load(float* dst, uint64_t* bar, const flo
     const float* src = strip + (long long)lo * kStepFloats;
     float* d = dst + (lo - sig_lo) * kStepFloats;
     if (kTMA) {
-        if (lane == 0) {
+        if (elect_one()) {
             // expect_copies same-sized copies complete on this barrier; the first one arms it
             if (expect_copies > 0) mbar_expect_tx(bar, (uint32_t)(expect_copies * nsteps) * kStepFloats * 4);
             tma_bulk_load(d, src, (uint32_t)nsteps * kStepFloats * 4, bar);

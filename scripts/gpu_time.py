@@ -36,7 +36,7 @@ def timeit(fn, iters=10):
 
 
 print(f"B={B} N={N} M={M}")
-configs = [(0, 0)] + [(W, G) for W in (1, 2, 4) for G in (0, 148 * 2, 148 * 4)]
+configs = [(0, 0), (1, 0), (2, 0), (1, 148 * 4), (4, 148 * 4)]
 for W, G in configs:
     fl = (W << 4) | (G << 8)
     try:
@@ -48,3 +48,19 @@ for W, G in configs:
                  cells / (f_ms + b_ms) / 1e6), flush=True)
     except Exception as e:  # noqa: BLE001
         print("W=%d grid=%d failed: %s" % (W, G, e), flush=True)
+
+# ---- host-side cost of the autograd path (no sync inside the timed parts) ----------
+from deepblast_b200.nw_cuda import NeedlemanWunschFunction as Fn  # noqa: E402
+th = theta.clone().requires_grad_()
+for _ in range(3):
+    v = Fn.apply(th, A, 'softmax'); g, = torch.autograd.grad(v.sum(), th)
+torch.cuda.synchronize()
+tf = ts = tg = 0.0
+n_it = 20
+for _ in range(n_it):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); v = Fn.apply(th, A, 'softmax'); t1 = time.perf_counter()
+    s = v.sum(); t2 = time.perf_counter()
+    g, = torch.autograd.grad(s, th); t3 = time.perf_counter()
+    tf += t1 - t0; ts += t2 - t1; tg += t3 - t2
+print("host ms per call: Function.apply %.3f  sum %.3f  autograd.grad %.3f" % (tf / n_it * 1e3, ts / n_it * 1e3, tg / n_it * 1e3))
