@@ -108,8 +108,8 @@ int check_common(const char* fn, int B, int N, int M) {
 
 // Launch geometry.  A pair is cut into K = ceil(N/32) strips; W warps of one CTA work
 // on one pair at a time.  Pick W (a power of two) and the grid so that the estimated
-// sweep time  ceil(B / grid) * ceil(K / W) * (M + 33)  is smallest; ties go to the
-// smaller W (fewer cross-warp hand-offs).
+// sweep time max(latency, throughput) is smallest (measured on B200: about 7 resident
+// warps per SM saturate the forward kernel); ties go to the smaller W (no hand-offs).
 struct Geometry {
     int W;
     int grid;
@@ -139,8 +139,14 @@ int pick_geometry(const char* fn, int B, int N, int M, int flags, SmemFn smem_of
         long long resident = (long long)di.sms * per_sm;
         int grid = (int)(B < resident ? B : resident);
         if (grid < 1) grid = 1;
+        // latency term: a pair's strips run back to back on its W warps; throughput term:
+        // the SM's issue/XU capacity is shared by all resident warps and does not depend
+        // on W, except for a few percent of hand-off cost per doubling
         double rounds = (double)((B + grid - 1) / grid);
-        double t = rounds * (double)((K + W - 1) / W) * (double)(M + 33);
+        double lat = rounds * (double)((K + W - 1) / W) * (double)(M + 33);
+        double thr = (double)B * K * (double)(M + 33) / ((double)di.sms * 7.0);
+        double pen = 1.0 + (W >= 2 ? 0.12 : 0.0) + (W >= 4 ? 0.05 : 0.0) + (W >= 8 ? 0.05 : 0.0);
+        double t = (lat > thr ? lat : thr) * pen;
         if (t < best * 0.999) {
             best = t;
             g.W = W;

@@ -148,6 +148,19 @@ __device__ __forceinline__ float fast_rcp(float x) {
     return y;
 }
 
+// 1/S for S in [1, 3] on the FMA pipe: cubic minimax seed in (S - 2) (relative error
+// 1.0e-2) and two Newton steps (1.6e-7, i.e. the accuracy of rcp.approx).  The XU pipe
+// (ex2 / lg2 / rcp) is the forward kernel's bottleneck on B200, the FMA pipe is not.
+__device__ __forceinline__ float rcp_1to3(float S) {
+    const float x = S - 2.0f;
+    float r = fmaf(-0.08242285f, x, 0.16481542f);
+    r = fmaf(r, x, -0.24747011f);
+    r = fmaf(r, x, 0.4949553f);
+    r = r * fmaf(-S, r, 2.0f);
+    r = r * fmaf(-S, r, 2.0f);
+    return r;
+}
+
 // ---- persistent strip iterator ---------------------------------------------------
 // A CTA owns pairs blockIdx.x, blockIdx.x + gridDim.x, ...; every pair is cut into
 // strips of 32 rows.  All strips of all the CTA's pairs form ONE linear sequence

@@ -41,14 +41,21 @@ __device__ __forceinline__ void fwd2_step(float th, float a, float uh, float ul,
     // u_x - u_m and u_y - u_m (nw.py:56-58) from the (hi, lo) pairs
     const float dx = ((uh - dh) + (ul - dl)) + a;
     const float dy = ((vh - dh) + (vl - dl)) + a;
-    const float mx = fmaxf(fmaxf(dx, dy), 0.f);
-    const float mxs = mx * kLog2e;
-    const float ex = fast_ex2(fmaf(dx, kLog2e, -mxs));
-    const float ey = fast_ex2(fmaf(dy, kLog2e, -mxs));
-    const float em = fast_ex2(-mxs);
-    const float S = (ex + em) + ey;
-    const float r = fast_rcp(S);
-    float qx = ex * r, qm = em * r, qy = ey * r;
+    // softmax / logsumexp over (dx, 0, dy), nw.py:10-27.  Relative to the maximum the
+    // largest term is exactly 1, so only two exponentials are evaluated (XU pipe), and
+    // 1/S with S in [1, 3] runs on the FMA pipe.
+    const float hi = fmaxf(dx, dy), lo = fminf(dx, dy);
+    const float mx = fmaxf(hi, 0.f);
+    const float e1 = fast_ex2(-fabsf(hi) * kLog2e);          // the smaller of exp(hi - mx), exp(0 - mx)
+    const float e2 = fast_ex2((lo - mx) * kLog2e);
+    const float S = (1.f + e1) + e2;
+    const float r = rcp_1to3(S);
+    const float e1r = e1 * r, e2r = e2 * r;
+    const bool hi_pos = hi >= 0.f, x_is_hi = dx >= dy;
+    const float qhi = hi_pos ? r : e1r;
+    float qm = hi_pos ? e1r : r;
+    float qx = x_is_hi ? qhi : e2r;
+    float qy = x_is_hi ? e2r : qhi;
     // V[i,j] = V[i-1,j-1] + (theta + logsumexp(dx, 0, dy))   (nw.py:59-60), Fast2Sum
     const float delta = th + fmaf(fast_lg2(S), kLn2, mx);
     const float t1 = delta + dl;

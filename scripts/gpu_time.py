@@ -64,3 +64,20 @@ for _ in range(n_it):
     g, = torch.autograd.grad(s, th); t3 = time.perf_counter()
     tf += t1 - t0; ts += t2 - t1; tg += t3 - t2
 print("host ms per call: Function.apply %.3f  sum %.3f  autograd.grad %.3f" % (tf / n_it * 1e3, ts / n_it * 1e3, tg / n_it * 1e3))
+
+# ---- do the kernels slow down when they alternate (as in a training step)? -------------
+def alt(iters=10):
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(iters)]
+    for it in range(iters):
+        ev[it][0].record()
+        Vt, Q = ops.forward_pass(theta, A, "nw")
+        ev[it][1].record()
+        E = ops.backward_pass(Et, Q, "nw", N=N)
+        ev[it][2].record()
+    torch.cuda.synchronize()
+    f = sum(e[0].elapsed_time(e[1]) for e in ev[2:]) / (iters - 2)
+    b = sum(e[1].elapsed_time(e[2]) for e in ev[2:]) / (iters - 2)
+    return f, b
+alt(4)
+f, b = alt(12)
+print("alternating C-ABI calls: fwd %.3f ms  bwd %.3f ms  -> %.1f Gcell/s" % (f, b, cells / (f + b) / 1e6))
