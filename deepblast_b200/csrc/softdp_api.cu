@@ -247,24 +247,31 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
                aligned(theta, 16) && aligned(A, 16);
     const bool fast = tma && !(flags & B200DP_V1_KERNELS) && !env_v1() && N >= kG && M >= 2 * kG;
     if (fast && encode_row_map(&tmT, theta, B, N, M, kG) && encode_row_map(&tmA, A, B, N, M, kG)) {
-        Geometry g2;
-        if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes, g2)) return rc;
+        // a 4-deep tile ring doubles the TMA lead; use it when it costs no residency
+        Geometry g3, g4;
+        if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<3>, g3)) return rc;
+        const bool ok4 = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<4>, g4) == 0;
+        int ring = (ok4 && g4.W == g3.W && g4.grid >= g3.grid) ? 4 : 3;
+        if (const char* e = getenv("B200DP_RING")) ring = atoi(e) == 4 && ok4 ? 4 : 3;
+        const Geometry g2 = ring == 4 ? g4 : g3;
         int dbg = 0;
         if (const char* e = getenv("B200DP_DBG")) dbg = atoi(e);     // diagnostics: see softdp_fwd2.cuh
+        int rc2 = 0;
+        auto run = [&](auto kern) {
+            rc2 = set_smem(kern, g2.smem, "b200dp_fwd");
+            if (!rc2) kern<<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmT, tmA, p);
+        };
+        const bool sw = mode == B200DP_MODE_SW;
         if (dbg >= 1 && dbg <= 3) {
-            auto run = [&](auto kern) {
-                if (set_smem(kern, g2.smem, "b200dp_fwd") == 0) kern<<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmT, tmA, p);
-            };
-            if (dbg == 1) run(softdp_fwd2_kernel<false, 1>);
-            else if (dbg == 2) run(softdp_fwd2_kernel<false, 2>);
-            else run(softdp_fwd2_kernel<false, 3>);
-        } else if (mode == B200DP_MODE_SW) {
-            if (int rc = set_smem(softdp_fwd2_kernel<true>, g2.smem, "b200dp_fwd")) return rc;
-            softdp_fwd2_kernel<true><<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmT, tmA, p);
+            if (dbg == 1) run(softdp_fwd2_kernel<false, 3, 1>);
+            else if (dbg == 2) run(softdp_fwd2_kernel<false, 3, 2>);
+            else run(softdp_fwd2_kernel<false, 3, 3>);
+        } else if (ring == 4) {
+            sw ? run(softdp_fwd2_kernel<true, 4>) : run(softdp_fwd2_kernel<false, 4>);
         } else {
-            if (int rc = set_smem(softdp_fwd2_kernel<false>, g2.smem, "b200dp_fwd")) return rc;
-            softdp_fwd2_kernel<false><<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmT, tmA, p);
+            sw ? run(softdp_fwd2_kernel<true, 3>) : run(softdp_fwd2_kernel<false, 3>);
         }
+        if (rc2) return rc2;
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) return cuda_fail(e2, "b200dp_fwd launch");
         return 0;

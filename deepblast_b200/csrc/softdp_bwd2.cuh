@@ -30,6 +30,27 @@ __host__ __device__ inline size_t bwd2_smem_bytes(int W, int M) {
     return b;
 }
 
+// Drain column tile tc (32 columns) of a strip from the step-major staging ring to the
+// row-major E tensor: lane = column, 32 independent LDS then 32 coalesced 128-byte
+// row-segment stores.  Element (r, col) was produced at step (m-1-col) + (31-r).
+__device__ __forceinline__ void bwd2_drain_tile(const float* __restrict__ stage, float* __restrict__ Erow0, int tc,
+                                                int m, int rmax, int pitch, int t) {
+    const int col = tc * kTile + t;
+    if (col >= m) return;
+    float* dstp = Erow0 + col + 1;
+    const int sr0 = (m - 1 - col + 31) % kB2StageSteps;
+    float v[kTile];
+#pragma unroll
+    for (int r = 0; r < kTile; ++r) {
+        int sr = sr0 - r;
+        sr += (sr < 0) ? kB2StageSteps : 0;
+        v[r] = stage[sr * kB2StagePitch + r];
+    }
+#pragma unroll
+    for (int r = 0; r < kTile; ++r)
+        if (r < rmax) dstp[(long long)r * pitch] = v[r];
+}
+
 template <bool SWM>
 __global__ void __launch_bounds__(256) softdp_bwd2_kernel(BwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -108,18 +129,8 @@ __global__ void __launch_bounds__(256) softdp_bwd2_kernel(BwdParams p) {
             // drain every column tile completed before this block: tile tc is complete
             // once lane 0 has passed column 32 tc, i.e. after step m + 30 - 32 tc
             while (next_drain >= 0 && (m + 30 - 32 * next_drain) < s0) {
-                const int tc = next_drain;
-                const int col = tc * kTile + t;
-                if (col < m) {
-                    float* dstp = Eb + (long long)(kb * kTile + 1) * (M + 2) + col + 1;
-                    const int rmax = min(kTile, n - kb * kTile);
-                    // element (r, col) was produced at step s = (m-1-col) + (31-r)
-                    int sr = (m - 1 - col + 31) % kB2StageSteps;
-                    for (int r = 0; r < rmax; ++r) {
-                        dstp[(long long)r * (M + 2)] = stage[sr * kB2StagePitch + r];
-                        sr = (sr == 0) ? kB2StageSteps - 1 : sr - 1;
-                    }
-                }
+                bwd2_drain_tile(stage, Eb + (long long)(kb * kTile + 1) * (M + 2), next_drain, m,
+                                min(kTile, n - kb * kTile), M + 2, t);
                 next_drain--;
             }
             __syncwarp();
@@ -184,17 +195,8 @@ __global__ void __launch_bounds__(256) softdp_bwd2_kernel(BwdParams p) {
         __syncwarp();
         // drain what is left (all steps are done)
         while (next_drain >= 0) {
-            const int tc = next_drain;
-            const int col = tc * kTile + t;
-            if (col < m) {
-                float* dstp = Eb + (long long)(kb * kTile + 1) * (M + 2) + col + 1;
-                const int rmax = min(kTile, n - kb * kTile);
-                int sr = (m - 1 - col + 31) % kB2StageSteps;
-                for (int r = 0; r < rmax; ++r) {
-                    dstp[(long long)r * (M + 2)] = stage[sr * kB2StagePitch + r];
-                    sr = (sr == 0) ? kB2StageSteps - 1 : sr - 1;
-                }
-            }
+            bwd2_drain_tile(stage, Eb + (long long)(kb * kTile + 1) * (M + 2), next_drain, m,
+                            min(kTile, n - kb * kTile), M + 2, t);
             next_drain--;
         }
         if (!varlen) {

@@ -17,13 +17,13 @@
 namespace b200dp {
 
 constexpr int kG = 16;                       // rows per group == columns per tile
-constexpr int kF2Ring = 3;                   // events resident: 2 live + 1 in flight
 constexpr int kF2SlotBytes = 4096;           // [2 groups][2 tensors][16][16] fp32
-constexpr int kF2WarpBytes = kF2Ring * kF2SlotBytes;
 
+// RING = events resident per warp: 2 live + (RING - 2) in flight (16 steps of lead each)
+template <int RING>
 __host__ __device__ inline size_t fwd2_smem_bytes(int W, int M) {
-    size_t b = (size_t)W * kF2WarpBytes;
-    b += (size_t)W * kF2Ring * 8;
+    size_t b = (size_t)W * RING * kF2SlotBytes;
+    b += (size_t)W * RING * 8;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)(W + 1) * 8;
     b = (b + 15) & ~(size_t)15;
@@ -85,7 +85,7 @@ __device__ __forceinline__ void fwd2_step(float th, float a, float uh, float ul,
     vl = nl;
 }
 
-template <bool SWM, int DBG = 0>
+template <bool SWM, int RING, int DBG = 0>
 __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant__ CUtensorMap tm_theta,
                                                           const __grid_constant__ CUtensorMap tm_A, FwdParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
     const int Mcap = p.d.M;
     const int g = t >> 4, tp = t & 15;
 
+    constexpr int kF2Ring = RING;
+    constexpr int kF2WarpBytes = RING * kF2SlotBytes;
     unsigned char* ring = smem_raw + (size_t)w * kF2WarpBytes;
     size_t off = (size_t)W * kF2WarpBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + off) + w * kF2Ring;
@@ -197,19 +199,26 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
             if (steady) {
                 const float2* br = has_up ? bnd_r + s0 : zero_row;
                 float2* bw = bw31 + s0;
+                // stage the block's operands in registers up front: 16 theta, 16 A and the
+                // 16 boundary pairs (uniform address, broadcast) -- one shared-memory
+                // latency per block instead of one per step on the dependent chain
+                float th_[16], a_[16];
+                float2 bv_[16];
+#pragma unroll
+                for (int ss = 0; ss < 16; ++ss) {
+                    const float* tb = (tp <= ss) ? baseB : baseA;
+                    th_[ss] = tb[ss];
+                    a_[ss] = tb[ss + 256];
+                    bv_[ss] = br[ss];
+                }
 #pragma unroll
                 for (int ss = 0; ss < 16; ++ss) {
                     float uh = __shfl_up_sync(kFull, vh, 1);
                     float ul = __shfl_up_sync(kFull, vl, 1);
-                    if (t == 0) {
-                        const float2 bv = br[ss];
-                        uh = bv.x;
-                        ul = bv.y;
-                    }
-                    const float* tb = (tp <= ss) ? baseB : baseA;
-                    const float th = tb[ss];
-                    const float a = tb[ss + 256];
-                    fwd2_step<false, false, DBG>(th, a, uh, ul, vh, vl, dh, dl, qp + ss * kStepFloats, true, true);
+                    uh = (t == 0) ? bv_[ss].x : uh;
+                    ul = (t == 0) ? bv_[ss].y : ul;
+                    fwd2_step<false, false, DBG>(th_[ss], a_[ss], uh, ul, vh, vl, dh, dl, qp + ss * kStepFloats, true,
+                                                 true);
                     if (t == 31 && feeds_down) bw[ss] = make_float2(vh, vl);
                 }
                 qp += 16 * kStepFloats;
