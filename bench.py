@@ -337,7 +337,7 @@ def main():
                        "l2": "inputs (theta+A %.0f MB, Q %.0f MB per GPU) exceed the 126 MB L2; no flush needed"
                              % (2 * Bg * N * M * 4 / 1e6, Bg * (N + 2) * (M + 2) * 12 / 1e6),
                        **({"packing": stats} if stats else {})},
-            "roofline": {"bound": "hbm", "kernel": f"softdp_{dom}_kernel", "achieved": ach, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": f"softdp_{dom}2_kernel", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_cell": BYTES_FWD if dom == "fwd" else BYTES_BWD,
                          "fwd": {"ms": fwd_ms, "GBps": fwd_gbs, "frac": fwd_gbs / peak},

@@ -31,24 +31,27 @@ __host__ __device__ inline size_t bwd2_smem_bytes(int W, int M) {
 }
 
 // Drain column tile tc (32 columns) of a strip from the step-major staging ring to the
-// row-major E tensor: lane = column, 32 independent LDS then 32 coalesced 128-byte
-// row-segment stores.  Element (r, col) was produced at step (m-1-col) + (31-r).
+// row-major E tensor: lane = column, 8 independent LDS then 8 coalesced 128-byte
+// row-segment stores at a time.  Element (r, col) was produced at step (m-1-col) + (31-r).
 __device__ __forceinline__ void bwd2_drain_tile(const float* __restrict__ stage, float* __restrict__ Erow0, int tc,
                                                 int m, int rmax, int pitch, int t) {
     const int col = tc * kTile + t;
     if (col >= m) return;
     float* dstp = Erow0 + col + 1;
     const int sr0 = (m - 1 - col + 31) % kB2StageSteps;
-    float v[kTile];
+#pragma unroll 1
+    for (int r0 = 0; r0 < rmax; r0 += 8) {
+        float v[8];
 #pragma unroll
-    for (int r = 0; r < kTile; ++r) {
-        int sr = sr0 - r;
-        sr += (sr < 0) ? kB2StageSteps : 0;
-        v[r] = stage[sr * kB2StagePitch + r];
+        for (int q = 0; q < 8; ++q) {
+            int sr = sr0 - (r0 + q);
+            sr += (sr < 0) ? kB2StageSteps : 0;
+            v[q] = stage[sr * kB2StagePitch + r0 + q];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (r0 + q < rmax) dstp[(long long)(r0 + q) * pitch] = v[q];
     }
-#pragma unroll
-    for (int r = 0; r < kTile; ++r)
-        if (r < rmax) dstp[(long long)r * pitch] = v[r];
 }
 
 template <bool SWM>
