@@ -240,8 +240,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    # warm-up: W untimed steps, with the rendezvous barrier exercised in between so that
+    # every lazy initialisation (NCCL communicator, allocator pools, autograd worker
+    # threads) happens before the timed region
+    for it in range(max(args.warmup, 3)):
         step()
+        if it == 0:
+            sync_all()
     sync_all()
 
     sampler = ClockSampler(local)
@@ -345,6 +350,7 @@ def main():
                          "step": {"GBps_at_36B_per_cell": step_gbs, "frac": step_gbs / peak}},
             "gpu_launches": 2 * args.steps,
             "host_enqueue_ms_per_step": host_ms,
+            "step_ms_median": float(np.median([k[0].elapsed_time(k[2]) for k in kev])),
             "clocks": clocks,
         }
         if e2e:

@@ -117,7 +117,8 @@ struct Geometry {
 };
 
 template <class SmemFn>
-int pick_geometry(const char* fn, int B, int N, int M, int flags, SmemFn smem_of, Geometry& g) {
+int pick_geometry(const char* fn, int B, int N, int M, int flags, SmemFn smem_of, Geometry& g,
+                  bool varlen = false) {
     DevInfo di;
     if (!dev_info(di)) return fail(-2, std::string(fn) + ": cannot query the CUDA device");
     const int K = (N + kTile - 1) / kTile;
@@ -129,6 +130,10 @@ int pick_geometry(const char* fn, int B, int N, int M, int flags, SmemFn smem_of
     g.W = 0;
     for (int W = 1; W <= 8; W *= 2) {
         if (forceW ? (W != forceW) : (W > 1 && W > K)) continue;
+        // ragged batches: the host does not know the lengths, but a CTA's strips form one
+        // sequence across pairs, so short pairs do not idle the warps of a wide CTA while
+        // long pairs need the width: keep the widest CTA that fits
+        if (!forceW && varlen && W < 8 && W < K && smem_of(2 * W, M) <= (size_t)di.smem_optin) continue;
         size_t smem = smem_of(W, M);
         if (smem > (size_t)di.smem_optin) continue;
         int per_sm = (int)((size_t)di.smem_per_sm / (smem + 1024));   // 1 KB reserved per CTA
@@ -229,7 +234,7 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
     if (!theta || !A || !Q || !Vt) return fail(-1, "b200dp_fwd: null pointer");
     if (!aligned(Q, 16)) return fail(-1, "b200dp_fwd: Q storage must be 16-byte aligned");
     Geometry g;
-    if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd_smem_bytes, g)) return rc;
+    if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd_smem_bytes, g, xlen || ylen)) return rc;
     FwdParams p;
     p.theta = theta;
     p.A = A;
@@ -249,8 +254,8 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
     if (fast && encode_row_map(&tmT, theta, B, N, M, kG) && encode_row_map(&tmA, A, B, N, M, kG)) {
         // a 4-deep tile ring doubles the TMA lead; use it when it costs no residency
         Geometry g3, g4;
-        if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<3>, g3)) return rc;
-        const bool ok4 = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<4>, g4) == 0;
+        if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<3>, g3, xlen || ylen)) return rc;
+        const bool ok4 = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<4>, g4, xlen || ylen) == 0;
         int ring = (ok4 && g4.W == g3.W && g4.grid >= g3.grid) ? 4 : 3;
         if (const char* e = getenv("B200DP_RING")) ring = atoi(e) == 4 && ok4 ? 4 : 3;
         const Geometry g2 = ring == 4 ? g4 : g3;
@@ -309,7 +314,7 @@ int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E, c
     const bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma();
     Geometry g;
     if (tma && !(flags & B200DP_V1_KERNELS) && !env_v1() && M >= 2 * kG) {
-        if (int rc = pick_geometry("b200dp_bwd", B, N, M, flags, bwd2_smem_bytes, g)) return rc;
+        if (int rc = pick_geometry("b200dp_bwd", B, N, M, flags, bwd2_smem_bytes, g, xlen || ylen)) return rc;
         if (mode == B200DP_MODE_SW) {
             if (int rc = set_smem(softdp_bwd2_kernel<true>, g.smem, "b200dp_bwd")) return rc;
             softdp_bwd2_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(p);
@@ -318,7 +323,7 @@ int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E, c
             softdp_bwd2_kernel<false><<<g.grid, 32 * g.W, g.smem, st>>>(p);
         }
     } else {
-        if (int rc = pick_geometry("b200dp_bwd", B, N, M, flags, bwd_smem_bytes, g)) return rc;
+        if (int rc = pick_geometry("b200dp_bwd", B, N, M, flags, bwd_smem_bytes, g, xlen || ylen)) return rc;
         if (tma) {
             if (int rc = set_smem(softdp_bwd_kernel<true>, g.smem, "b200dp_bwd")) return rc;
             softdp_bwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(p);
@@ -340,7 +345,7 @@ int b200dp_adj_fwd(const float* Q, const float* Ztheta, const float* ZA, float* 
     if (!aligned(Q, 16) || !aligned(Qd, 16))
         return fail(-1, "b200dp_adj_fwd: Q/Qd storage must be 16-byte aligned");
     Geometry g;
-    if (int rc = pick_geometry("b200dp_adj_fwd", B, N, M, flags, adj_fwd_smem_bytes, g)) return rc;
+    if (int rc = pick_geometry("b200dp_adj_fwd", B, N, M, flags, adj_fwd_smem_bytes, g, xlen || ylen)) return rc;
     AdjFwdParams p;
     p.Q = Q;
     p.Ztheta = Ztheta;
@@ -370,7 +375,7 @@ int b200dp_adj_bwd(const float* E, const float* Q, const float* Qd, float* Ed, c
     if (!aligned(Q, 16) || !aligned(Qd, 16))
         return fail(-1, "b200dp_adj_bwd: Q/Qd storage must be 16-byte aligned");
     Geometry g;
-    if (int rc = pick_geometry("b200dp_adj_bwd", B, N, M, flags, adj_bwd_smem_bytes, g)) return rc;
+    if (int rc = pick_geometry("b200dp_adj_bwd", B, N, M, flags, adj_bwd_smem_bytes, g, xlen || ylen)) return rc;
     AdjBwdParams p;
     p.E = E;
     p.Q = Q;

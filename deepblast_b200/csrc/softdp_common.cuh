@@ -173,6 +173,7 @@ struct Strip {
     int k;        // strip ordinal inside the pair in PROCESSING order (0 = first processed)
     int K;        // strips in the pair
     int n, m;     // lattice of the pair
+    int round;    // how many pairs this CTA has been dealt
     unsigned q;   // linear sequence number inside the CTA
     bool valid;
 };
@@ -195,7 +196,11 @@ __device__ __forceinline__ void strip_seek(Strip& s, const PairDims& d, int w, i
             return;
         }
         if (s.k >= s.K) {
-            s.pair += gridDim.x;
+            // next round, boustrophedon: rounds alternate direction so that a batch sorted
+            // by descending work is dealt evenly to the CTAs
+            s.round++;
+            const int lane = (s.round & 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+            s.pair = s.round * (int)gridDim.x + lane;
             s.k = 0;
             if (s.pair < d.B) strip_load_pair(s, d);
             continue;
@@ -210,6 +215,7 @@ __device__ __forceinline__ void strip_seek(Strip& s, const PairDims& d, int w, i
 }
 __device__ __forceinline__ void strip_first(Strip& s, const PairDims& d, int w, int W) {
     s.pair = blockIdx.x;
+    s.round = 0;
     s.k = 0;
     s.q = 0;
     s.K = 0;

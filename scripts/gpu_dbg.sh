@@ -1,7 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-echo "== B=2048 (W=1 -> 14 warps/SM)"; timeout 200 python -u scripts/gpu_time.py 2048 256 256 2>&1 | grep -E "^W=|alternating"
-echo "== B=4096"; timeout 200 python -u scripts/gpu_time.py 4096 256 256 2>&1 | grep -E "^W=0|^W=1 grid=0|alternating"
-echo "== B=1024 512x512"; timeout 200 python -u scripts/gpu_time.py 1024 512 512 2>&1 | grep -E "^W=0|^W=1 grid=0|^W=2 grid=0|alternating"
-} 2>&1 | tee gpurun_out/dbg.log
+echo "== single process"; timeout 120 python -u scripts/dbg_2gpu.py
+echo "== single process OMP=1"; OMP_NUM_THREADS=1 timeout 120 python -u scripts/dbg_2gpu.py
+echo "== torchrun 2, with PG"; timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 scripts/dbg_2gpu.py
+echo "== torchrun 2, no PG"; NO_PG=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 scripts/dbg_2gpu.py
+} 2>&1 | grep -v "^\*\*\*\|OMP_NUM_THREADS env\|^$" | tee gpurun_out/dbg2.log
