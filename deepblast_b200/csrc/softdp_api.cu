@@ -15,8 +15,10 @@
 #include "softdp_adjoint.cuh"
 #include "softdp_bwd.cuh"
 #include "softdp_bwd2.cuh"
+#include "softdp_bwd3.cuh"
 #include "softdp_fwd.cuh"
 #include "softdp_fwd2.cuh"
+#include "softdp_fwd3.cuh"
 #include "softdp_traceback.cuh"
 
 using namespace b200dp;
@@ -79,12 +81,12 @@ bool dev_info(DevInfo& out) {
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // rank-3 map over a contiguous [B, N, M] fp32 tensor, box 32 cols x 32 rows x 1
-bool encode_row_map(CUtensorMap* map, const float* ptr, int B, int N, int M, int boxdim = kTile) {
+bool encode_row_map(CUtensorMap* map, const float* ptr, int B, int N, int M, int boxdim = kTile, int boxrows = 0) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)M, (cuuint64_t)N, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)M * 4, (cuuint64_t)N * M * 4};
-    cuuint32_t box[3] = {(cuuint32_t)boxdim, (cuuint32_t)boxdim, 1};
+    cuuint32_t box[3] = {(cuuint32_t)boxdim, (cuuint32_t)(boxrows ? boxrows : boxdim), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -95,8 +97,11 @@ bool encode_row_map(CUtensorMap* map, const float* ptr, int B, int N, int M, int
 QLayout q_layout(int N, int M) {
     QLayout ql;
     ql.K = (N + kTile - 1) / kTile;
-    ql.strip_stride = (long long)(M + 31) * kStepFloats;
-    ql.pair_stride = ql.K * ql.strip_stride;
+    // chained-dense: strip k+1 starts M steps after strip k, so the 31 ramp steps of
+    // consecutive strips interleave lane-wise (strip k's tail uses lanes t > sigma - M of a
+    // step, strip k+1's head lanes t <= sigma - M) and no step is padding
+    ql.strip_stride = (long long)M * kStepFloats;
+    ql.pair_stride = ql.K * ql.strip_stride + 31 * kStepFloats;
     return ql;
 }
 
@@ -208,6 +213,161 @@ bool env_v1() {
     return e && atoi(e) != 0;
 }
 
+// Chained backward kernel (softdp_bwd3.cuh).  Same return convention as launch_fwd3.
+template <int RING>
+int launch_bwd3_t(const BwdParams& p, int grid, size_t smem, bool sw, cudaStream_t st) {
+    int rc = 0;
+    auto run = [&](auto kern) {
+        rc = set_smem(kern, smem, "b200dp_bwd");
+        if (!rc) kern<<<grid, 32, smem, st>>>(p);
+    };
+    if (sw) run(softdp_bwd3_kernel<true, RING>);
+    else run(softdp_bwd3_kernel<false, RING>);
+    return rc;
+}
+
+int launch_bwd3(const BwdParams& p, int B, int N, int M, int mode, int flags, cudaStream_t st) {
+    if (const char* e = getenv("B200DP_V3")) if (atoi(e) == 0) return 1;
+    DevInfo di;
+    if (!dev_info(di)) return 1;
+    int minB = 2 * di.sms;
+    if (const char* e = getenv("B200DP_V3MIN")) minB = atoi(e);
+    if (B < minB || N < kTile || M < 64 || M % 32 != 0) return 1;
+    int want_ring = 0;
+    if (const char* e = getenv("B200DP_BRING")) want_ring = atoi(e);
+    int forceG = (flags >> B200DP_CTAS_SHIFT) & 0xFFFF;
+    if (const char* e = getenv("B200DP_CTAS")) forceG = atoi(e);
+    const int rings[4] = {3, 4, 6, 2};     // measured on B200: 3 slots win
+    int ring = 0, grid = 0;
+    size_t smem = 0;
+    long long best_rounds = 0;
+    for (int ri = 0; ri < 4; ++ri) {
+        const int r = rings[ri];
+        if (want_ring ? (r != want_ring) : (r == 2)) continue;
+        const size_t sm = (size_t)r * kDiagElems * 4 + kB3StageBytes + (size_t)r * 8 + 16 + (size_t)M * 4 + 128;
+        if (sm > (size_t)di.smem_optin) continue;
+        int per_sm = (int)((size_t)di.smem_per_sm / (sm + 1024));
+        if (per_sm > 32) per_sm = 32;
+        if (per_sm < 1) continue;
+        const long long resident = (long long)di.sms * per_sm;
+        const long long rounds = (B + resident - 1) / resident;
+        if (!ring || rounds < best_rounds) {
+            ring = r;
+            grid = (int)((B + rounds - 1) / rounds);
+            smem = sm;
+            best_rounds = rounds;
+        }
+    }
+    if (!ring) return 1;
+    if (forceG > 0) grid = forceG;
+    const bool sw = mode == B200DP_MODE_SW;
+    int rc = 0;
+    if (ring == 6) rc = launch_bwd3_t<6>(p, grid, smem, sw, st);
+    else if (ring == 4) rc = launch_bwd3_t<4>(p, grid, smem, sw, st);
+    else if (ring == 3) rc = launch_bwd3_t<3>(p, grid, smem, sw, st);
+    else rc = launch_bwd3_t<2>(p, grid, smem, sw, st);
+    if (rc) return -(1000 + rc);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -(1000 + cuda_fail(e, "b200dp_bwd launch"));
+    return 0;
+}
+
+// Chained forward kernel: one warp per CTA, NCH strips side by side, RING tile slots.
+// Returns 0 when launched, > 0 when the shape / batch is not for this kernel (the caller
+// falls through to softdp_fwd2), < 0 (-(1000 + code)) on error.
+template <int NCH, int RING>
+int launch_fwd3_t(const CUtensorMap& tmT, const CUtensorMap& tmA, const CUtensorMap& pfT, const CUtensorMap& pfA,
+                  const FwdParams& p, int grid, size_t smem, bool sw, int dbg, cudaStream_t st) {
+    int rc = 0;
+    auto run = [&](auto kern) {
+        rc = set_smem(kern, smem, "b200dp_fwd");
+        if (!rc) kern<<<grid, 32, smem, st>>>(tmT, tmA, pfT, pfA, p);
+    };
+    if (dbg == 1) run(softdp_fwd3_kernel<false, NCH, RING, 1>);
+    else if (dbg == 2) run(softdp_fwd3_kernel<false, NCH, RING, 2>);
+    else if (dbg == 3) run(softdp_fwd3_kernel<false, NCH, RING, 3>);
+    else if (sw) run(softdp_fwd3_kernel<true, NCH, RING>);
+    else run(softdp_fwd3_kernel<false, NCH, RING>);
+    return rc;
+}
+
+int launch_fwd3(const CUtensorMap& tmT, const CUtensorMap& tmA, FwdParams p, int B, int N, int M, int mode,
+                int flags, cudaStream_t st) {
+    if (const char* e = getenv("B200DP_V3")) if (atoi(e) == 0) return 1;
+    DevInfo di;
+    if (!dev_info(di)) return 1;
+    int minB = 2 * di.sms;
+    if (const char* e = getenv("B200DP_V3MIN")) minB = atoi(e);
+    if (B < minB || N < kTile) return 1;
+    const int K = (N + kTile - 1) / kTile;
+    int nch = 1;     // measured on B200: two chains per warp lose to one (the kernel is bound by the memory system, not by issue latency)
+    if (const char* e = getenv("B200DP_NCH")) nch = atoi(e) == 2 ? 2 : 1;
+    if (M < 32 * nch + 32) nch = 1;
+    if (M < 64) return 1;
+    int want_ring = 0;
+    if (const char* e = getenv("B200DP_RING")) want_ring = atoi(e);
+    int forceG = (flags >> B200DP_CTAS_SHIFT) & 0xFFFF;
+    if (const char* e = getenv("B200DP_CTAS")) forceG = atoi(e);
+    int dbg = 0;
+    if (const char* e = getenv("B200DP_DBG")) dbg = atoi(e);
+    // measured on B200: the shallow ring wins (3 slots = one event of lead)
+    const int rings[4] = {3, 4, 6, 8};
+    int ring = 0, grid = 0;
+    size_t smem = 0;
+    long long best_rounds = 0;
+    for (int ri = 0; ri < 4; ++ri) {
+        const int r = rings[ri];
+        if (want_ring && r != want_ring) continue;
+        const size_t sm = (size_t)r * nch * 4096 + (size_t)r * 8 + 16 + (size_t)M * 4 + 128;
+        if (sm > (size_t)di.smem_optin) continue;
+        int per_sm = (int)((size_t)di.smem_per_sm / (sm + 1024));
+        if (per_sm > 32) per_sm = 32;
+        if (per_sm < 1) continue;
+        const long long resident = (long long)di.sms * per_sm;
+        // equal number of pairs per CTA: rounds = ceil(B / resident), grid = ceil(B / rounds);
+        // fewer rounds = more chains resident wins, among equals the ring tried first
+        const long long rounds = (B + resident - 1) / resident;
+        if (!ring || rounds < best_rounds) {
+            ring = r;
+            grid = (int)((B + rounds - 1) / rounds);
+            smem = sm;
+            best_rounds = rounds;
+        }
+    }
+    if (!ring) return 1;
+    if (forceG > 0) grid = forceG;
+    // optional wide L2 prefetch boxes (B200DP_PFW columns x 32 nch rows, B200DP_PFD tiles ahead)
+    int pfw = 0, pfd = 8;
+    if (const char* e = getenv("B200DP_PFW")) pfw = atoi(e);
+    if (const char* e = getenv("B200DP_PFD")) pfd = atoi(e);
+    CUtensorMap pfT, pfA;
+    memset(&pfT, 0, sizeof(pfT));
+    memset(&pfA, 0, sizeof(pfA));
+    p.pf_tiles = 0;
+    p.pf_dist = 0;
+    if (pfw >= 16 && pfw <= 256 && pfw % 16 == 0 && M % pfw == 0 && pfd >= 0 &&
+        encode_row_map(&pfT, p.theta, B, N, M, pfw, 32 * nch) && encode_row_map(&pfA, p.A, B, N, M, pfw, 32 * nch)) {
+        p.pf_tiles = pfw / 16;
+        p.pf_dist = pfd;
+    } else {
+        pfT = tmT;
+        pfA = tmA;
+    }
+    const bool sw = mode == B200DP_MODE_SW;
+    int rc = 0;
+#define B200DP_F3(NCH_, RING_) rc = launch_fwd3_t<NCH_, RING_>(tmT, tmA, pfT, pfA, p, grid, smem, sw, dbg, st)
+    if (nch == 2) {
+        if (ring == 8) B200DP_F3(2, 8); else if (ring == 6) B200DP_F3(2, 6); else if (ring == 4) B200DP_F3(2, 4); else B200DP_F3(2, 3);
+    } else {
+        if (ring == 8) B200DP_F3(1, 8); else if (ring == 6) B200DP_F3(1, 6); else if (ring == 4) B200DP_F3(1, 4); else B200DP_F3(1, 3);
+    }
+#undef B200DP_F3
+    if (rc) return -(1000 + rc);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return -(1000 + cuda_fail(e, "b200dp_fwd launch"));
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -244,6 +404,8 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
     p.ql = q_layout(N, M);
     p.i0 = mode == B200DP_MODE_SW ? 2 : 1;
     p.flags = flags;
+    p.pf_tiles = 0;
+    p.pf_dist = 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CUtensorMap tmT, tmA;
     memset(&tmT, 0, sizeof(tmT));
@@ -252,13 +414,38 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
                aligned(theta, 16) && aligned(A, 16);
     const bool fast = tma && !(flags & B200DP_V1_KERNELS) && !env_v1() && N >= kG && M >= 2 * kG;
     if (fast && encode_row_map(&tmT, theta, B, N, M, kG) && encode_row_map(&tmA, A, B, N, M, kG)) {
-        // a 4-deep tile ring doubles the TMA lead; use it when it costs no residency
-        Geometry g3, g4;
-        if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<3>, g3, xlen || ylen)) return rc;
-        const bool ok4 = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<4>, g4, xlen || ylen) == 0;
-        int ring = (ok4 && g4.W == g3.W && g4.grid >= g3.grid) ? 4 : 3;
-        if (const char* e = getenv("B200DP_RING")) ring = atoi(e) == 4 && ok4 ? 4 : 3;
-        const Geometry g2 = ring == 4 ? g4 : g3;
+        // large batches of equal-size lattices: chained single-warp kernel (softdp_fwd3.cuh)
+        if (!xlen && !ylen && M % 16 == 0 && !((flags >> B200DP_WARPS_SHIFT) & 0xF) && !getenv("B200DP_WARPS")) {
+            int rc3 = launch_fwd3(tmT, tmA, p, B, N, M, mode, flags, st);
+            if (rc3 <= 0) return rc3 < 0 ? -rc3 - 1000 : 0;    // 0 = launched, < 0 = error, > 0 = not applicable
+        }
+        // a deeper tile ring lengthens the TMA lead (RING - 2 events of 16 steps); take the
+        // deepest ring that costs no residency (read latency under the kernel's own write
+        // traffic is several microseconds)
+        Geometry g2;
+        if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<3>, g2, xlen || ylen)) return rc;
+        int ring = 3;
+        {
+            int want = 8;
+            if (const char* e = getenv("B200DP_RING")) want = atoi(e);
+            Geometry gt;
+            if (want >= 4 && pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<4>, gt, xlen || ylen) == 0 &&
+                gt.W == g2.W && gt.grid >= g2.grid) {
+                ring = 4;
+                g2 = gt;
+                if (want >= 6 && pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<6>, gt, xlen || ylen) == 0 &&
+                    gt.W == g2.W && gt.grid >= g2.grid) {
+                    ring = 6;
+                    g2 = gt;
+                    if (want >= 8 &&
+                        pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<8>, gt, xlen || ylen) == 0 &&
+                        gt.W == g2.W && gt.grid >= g2.grid) {
+                        ring = 8;
+                        g2 = gt;
+                    }
+                }
+            }
+        }
         int dbg = 0;
         if (const char* e = getenv("B200DP_DBG")) dbg = atoi(e);     // diagnostics: see softdp_fwd2.cuh
         int rc2 = 0;
@@ -268,9 +455,16 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
         };
         const bool sw = mode == B200DP_MODE_SW;
         if (dbg >= 1 && dbg <= 3) {
+            Geometry g3;
+            if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<3>, g3, xlen || ylen)) return rc;
+            g2 = g3;
             if (dbg == 1) run(softdp_fwd2_kernel<false, 3, 1>);
             else if (dbg == 2) run(softdp_fwd2_kernel<false, 3, 2>);
             else run(softdp_fwd2_kernel<false, 3, 3>);
+        } else if (ring == 8) {
+            sw ? run(softdp_fwd2_kernel<true, 8>) : run(softdp_fwd2_kernel<false, 8>);
+        } else if (ring == 6) {
+            sw ? run(softdp_fwd2_kernel<true, 6>) : run(softdp_fwd2_kernel<false, 6>);
         } else if (ring == 4) {
             sw ? run(softdp_fwd2_kernel<true, 4>) : run(softdp_fwd2_kernel<false, 4>);
         } else {
@@ -313,6 +507,12 @@ int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E, c
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma();
     Geometry g;
+    if (tma && !(flags & B200DP_V1_KERNELS) && !env_v1() && !xlen && !ylen && !((flags >> B200DP_WARPS_SHIFT) & 0xF) &&
+        !getenv("B200DP_WARPS")) {
+        // large batches of equal-size lattices: chained single-warp kernel (softdp_bwd3.cuh)
+        int rc3 = launch_bwd3(p, B, N, M, mode, flags, st);
+        if (rc3 <= 0) return rc3 < 0 ? -rc3 - 1000 : 0;
+    }
     if (tma && !(flags & B200DP_V1_KERNELS) && !env_v1() && M >= 2 * kG) {
         if (int rc = pick_geometry("b200dp_bwd", B, N, M, flags, bwd2_smem_bytes, g, xlen || ylen)) return rc;
         if (mode == B200DP_MODE_SW) {

@@ -1,0 +1,293 @@
+// softdp_bwd3.cuh -- backward sweep, CHAINED fast path for large batches of equal-size
+// lattices (reference: deepblast/nw.py:120-135, sw.py:100-115; replaces
+// deepblast/nw_cuda.py:82-102).
+//
+// Same push-form step as softdp_bwd2.cuh, organised like softdp_fwd3.cuh: one warp per
+// CTA, no hand-offs, and the wavefront never drains.  The strips of all the CTA's pairs
+// (each pair bottom-up) form one linear sequence of segments of M columns swept right to
+// left; at step S lane t (u = 31 - t, lane 31 leads) sits at linear position S - u, and a
+// lane that finishes its row starts the same row of the strip above on the next step.
+//   * Q: in the chained strip-major layout (strip_stride = M steps) the line of wavefront
+//     step sigma of strip kb+1 IS the line of step sigma + M of strip kb, so every lane of
+//     the warp -- whichever of two strips it is in -- reads the same 384-byte line, and the
+//     sweep walks a pair's Q storage sequentially from its end to its beginning: one 6 KB
+//     1-D bulk-TMA tile per 16 steps.  Only at a pair boundary two tiles are live (the
+//     first 31 lines of the old pair, the last lines of the new one).
+//   * E is staged step-major (pitch 33) and complete 32-column tiles are drained row-major
+//     exactly as in softdp_bwd2.cuh; in linear time one tile completes every 32 steps.
+//   * the row below a strip (what lane 0 of the previous segment pushed up) lives in one
+//     boundary row of M floats per warp.
+// Requirements (checked by the host): no per-pair lengths, M % 32 == 0, M >= 64.
+#pragma once
+#include "softdp_bwd2.cuh"
+
+namespace b200dp {
+
+constexpr int kB3StageBytes = ((kB2StageFloats * 4 + 127) / 128) * 128;
+
+template <int RING>
+__host__ __device__ inline size_t bwd3_smem_bytes(int M) {
+    size_t b = (size_t)RING * kDiagElems * 4 + kB3StageBytes;
+    b += (size_t)RING * 8;
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)M * 4;                            // boundary row
+    b += 128;                                      // 16 zeros + slack
+    return b;
+}
+
+// Drain column tile tc of the segment whose first step had staging row `segrow`
+// (= (segment * M) mod 80): element (r, col) was produced at segment step
+// (M-1-col) + (31-r).  lane = column; 8 independent LDS then 8 coalesced stores.
+__device__ __forceinline__ void bwd3_drain_tile(const float* __restrict__ stage, float* __restrict__ Erow0, int tc,
+                                                int M, int rmax, int pitch, int t, int segrow) {
+    const int col = tc * kTile + t;
+    float* dstp = Erow0 + col + 1;
+    const int sr0 = (segrow + (M - 1 - col) + 31) % kB2StageSteps;
+#pragma unroll 1
+    for (int r0 = 0; r0 < rmax; r0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            int sr = sr0 - (r0 + q);
+            sr += (sr < 0) ? kB2StageSteps : 0;
+            v[q] = stage[sr * kB2StagePitch + r0 + q];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (r0 + q < rmax) dstp[(long long)(r0 + q) * pitch] = v[q];
+    }
+}
+
+template <bool SWM, int RING>
+__global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int t = threadIdx.x, u = 31 - t;
+    const int N = p.d.N, M = p.d.M, B = p.d.B;
+    const int K = (N + 31) >> 5, T32 = M >> 5;
+    const int TA = (K * M) >> 4;                  // 16-step blocks (= main Q tiles) per pair
+
+    float* qring = reinterpret_cast<float*>(smem_raw);
+    float* stage = qring + RING * kDiagElems;
+    size_t off = (size_t)RING * kDiagElems * 4 + kB3StageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + off);
+    off = (off + (size_t)RING * 8 + 15) & ~(size_t)15;
+    float* bnd = reinterpret_cast<float*>(smem_raw + off);
+    float* zero_row = bnd + M;
+
+    if (t == 0)
+        for (int s = 0; s < RING; ++s) mbar_init(&bars[s], 1);
+    if (t < 16) zero_row[t] = 0.f;
+    fence_mbar_init();
+    __syncthreads();
+
+    const int grid = (int)gridDim.x, bid = (int)blockIdx.x;
+    const int R = B / grid, rem = B - R * grid;
+    const int npairs = R + ((((R & 1) ? grid - 1 - bid : bid) < rem) ? 1 : 0);
+    if (npairs == 0) return;
+    auto pair_of = [&](int r) { return r * grid + ((r & 1) ? grid - 1 - bid : bid); };
+    const int G = npairs * K;                     // segments (strips) of this CTA
+    const int NBLK = npairs * TA + 2;             // 16-step blocks until lane 0 is done
+    const int NDRAIN = G * T32;                   // 32-column E tiles to drain
+    const long long PS = p.ql.pair_stride;
+    const long long Epair = (long long)(N + 2) * (M + 2);
+    const int tlast = (N - 1) & 31;
+
+    // ---- Q tile stream: block bb of pair idx = bb / TA needs main tile a = bb % TA of that
+    // pair and, while a < 2 and idx >= 1, tail tile TA + a of the previous pair ---------------
+    int iss_idx = 0, iss_a = 0, iss_sub = 0, iss_cnt = 0, con_cnt = 0;
+    unsigned islot = 0, wslot = 0, phases = 0;
+    auto next_tile = [&](int& pr, int& tile) -> bool {
+        for (;;) {
+            if (iss_idx > npairs || (iss_idx == npairs && iss_a >= 2)) return false;
+            if (iss_sub == 0) {
+                iss_sub = 1;
+                if (iss_idx < npairs) {
+                    pr = iss_idx;
+                    tile = iss_a;
+                    return true;
+                }
+            } else {
+                const bool tail = iss_a < 2 && iss_idx >= 1;
+                const int pi = iss_idx - 1, ta = TA + iss_a;
+                iss_sub = 0;
+                if (++iss_a == TA) {
+                    iss_a = 0;
+                    ++iss_idx;
+                }
+                if (tail) {
+                    pr = pi;
+                    tile = ta;
+                    return true;
+                }
+            }
+        }
+    };
+    auto wait_tile = [&]() -> const float* {
+        mbar_wait(&bars[wslot], (phases >> wslot) & 1u);
+        phases ^= 1u << wslot;
+        const float* s = qring + wslot * kDiagElems;
+        wslot = (wslot + 1 == RING) ? 0u : wslot + 1;
+        return s;
+    };
+
+    // ---- sweep state -------------------------------------------------------------------------
+    float zout = 0.f, dprev = 0.f, yprev = 0.f;
+    int posS = 0, gL = 0, idxL = 0, kL = 0, a = 0;      // leading edge: segment, pair ordinal, strip ordinal (0 = bottom), block in pair
+    int idxT = 0, kT = 0;                                // the segment before it
+    int srow = 0;                                        // (16 b) mod 80
+    int drained = 0, d_idx = 0, d_k = 0, d_tc = T32 - 1, d_segrow = 0;
+
+    auto drain_ready = [&](int S0) {
+        // the n-th tile in drain order is complete once the sweep has passed step 64 + 32 n
+        while (drained < NDRAIN && 64 + 32 * drained <= S0) {
+            const int pair = pair_of(d_idx);
+            const int kb = K - 1 - d_k;
+            float* Eb = p.E + (long long)pair * Epair;
+            bwd3_drain_tile(stage, Eb + (long long)(kb * kTile + 1) * (M + 2), d_tc, M, min(kTile, N - kb * kTile),
+                            M + 2, t, d_segrow);
+            drained++;
+            if (--d_tc < 0) {
+                // strip complete: zero borders, E[N+1, M+1] = Et  (nw.py:125-127, 347)
+                const int i = kb * kTile + t + 1;
+                if (i <= N) {
+                    Eb[(long long)i * (M + 2)] = 0.f;
+                    Eb[(long long)i * (M + 2) + M + 1] = 0.f;
+                }
+                if (kb == 0)
+                    for (int col = t; col < M + 2; col += 32) Eb[col] = 0.f;
+                if (d_k == 0) {
+                    const float et = p.Et[(long long)pair * p.et_stride];
+                    for (int col = t; col < M + 2; col += 32)
+                        Eb[(long long)(N + 1) * (M + 2) + col] = (col == M + 1) ? et : 0.f;
+                }
+                d_tc = T32 - 1;
+                d_segrow = (d_segrow + M) % kB2StageSteps;
+                if (++d_k == K) {
+                    d_k = 0;
+                    ++d_idx;
+                }
+            }
+        }
+    };
+
+    for (int b = 0; b < NBLK; ++b) {
+        __syncwarp();
+        {
+            int pr, tile;
+            while (iss_cnt - con_cnt < RING && next_tile(pr, tile)) {
+                q_tile_load<true>(qring + islot * kDiagElems, &bars[islot], p.Q + (long long)pair_of(pr) * PS,
+                                  K * M + 15 - kDiagRows * tile, t);
+                islot = (islot + 1 == RING) ? 0u : islot + 1;
+                iss_cnt++;
+            }
+        }
+        const bool has_main = idxL < npairs;
+        const bool has_tail = a < 2 && idxL >= 1;
+        const float* qmain = nullptr;
+        const float* qtail = nullptr;
+        if (has_main) qmain = wait_tile();
+        if (has_tail) qtail = wait_tile();
+        if (!has_main) qmain = qtail;
+        if (!has_tail) qtail = qmain;
+        const int S0 = b * 16;
+        drain_ready(S0);
+        __syncwarp();
+
+        const bool plain = posS >= 32;              // every lane is in segment gL
+        const bool Lvalid = gL < G;
+        const int kbL = K - 1 - kL;
+        const bool fullL = (kbL + 1) * kTile <= N;
+        const float* br = (Lvalid && kL > 0) ? bnd + posS : zero_row;
+        float* st = stage + srow * kB2StagePitch + t;
+        const bool sw_special = SWM && (kbL == 0 || posS == M - 16);
+
+        if (plain && Lvalid && fullL && !sw_special) {
+            // ---- steady block ---------------------------------------------------------------
+            const float* qt = qmain + t;
+            float* bw = bnd + (posS - 31);
+            float bv_[16];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 b4 = reinterpret_cast<const float4*>(br)[q4];
+                bv_[4 * q4] = b4.x;
+                bv_[4 * q4 + 1] = b4.y;
+                bv_[4 * q4 + 2] = b4.z;
+                bv_[4 * q4 + 3] = b4.w;
+            }
+#pragma unroll
+            for (int ss = 0; ss < 16; ++ss) {
+                float zin = __shfl_down_sync(kFull, zout, 1);
+                if (t == 31) zin = bv_[ss];
+                const float e = zin + yprev;
+                const float X = qt[(15 - ss) * 96] * e;
+                const float D = qt[(15 - ss) * 96 + 32] * e;
+                const float Y = qt[(15 - ss) * 96 + 64] * e;
+                st[ss * kB2StagePitch] = e;
+                zout = X + dprev;
+                dprev = D;
+                yprev = Y;
+                if (t == 0) bw[ss] = zout;
+            }
+        } else {
+            // ---- general block: two segments, start / end of the sequence, partial strips.
+            // Q of cells outside the lattice was never written (arbitrary bits): products
+            // are selected, not multiplied by zero. -----------------------------------------
+            const bool Tvalid = plain ? Lvalid : (gL >= 1 && gL - 1 < G);
+            const int kbT = K - 1 - (plain ? kL : kT);
+            const int roll = plain ? -64 : (u - posS);         // step at which the lane enters L
+            const bool okL = Lvalid && kbL * kTile + t < N;
+            const bool okT = Tvalid && kbT * kTile + t < N;
+            const bool seedL = Lvalid && kL == 0 && t == tlast;
+            const float etL = Lvalid ? p.Et[(long long)pair_of(idxL) * p.et_stride] : 0.f;
+            const int shat = 16 * a;                            // local step of the leading edge in pair idxL
+#pragma unroll 4
+            for (int ss = 0; ss < 16; ++ss) {
+                float zin = __shfl_down_sync(kFull, zout, 1);
+                if (t == 31) zin = br[ss];
+                const bool inL = ss >= roll;
+                const bool at = ss == roll;                     // last column of the lane's new row
+                yprev = at ? 0.f : yprev;
+                dprev = at ? 0.f : dprev;
+                const bool ok = inL ? okL : okT;
+                float e = zin + yprev;
+                if (at && seedL) e = etL;                       // E[N, M] = Et  (nw.py:125-127)
+                bool comp = ok;
+                if (SWM) {
+                    const int o = posS + ss - u + (inL ? 0 : M);      // columns swept in this row so far
+                    const int kb = inL ? kbL : kbT;
+                    comp = ok && o != M - 1 && !(kb == 0 && t == 0);  // sw.py: i, j >= 2
+                }
+                e = comp ? e : 0.f;
+                const float* qt = ((has_tail && u > shat + ss) ? qtail : qmain) + t + (15 - ss) * 96;
+                const float X = comp ? qt[0] * e : 0.f;
+                const float D = comp ? qt[32] * e : 0.f;
+                const float Y = comp ? qt[64] * e : 0.f;
+                st[ss * kB2StagePitch] = e;
+                zout = X + dprev;
+                dprev = D;
+                yprev = Y;
+                if (t == 0) bnd[posS + ss - 31 + (inL ? 0 : M)] = zout;
+            }
+        }
+        con_cnt += (has_main ? 1 : 0) + ((a < 2 && idxL >= 1) ? 1 : 0);
+        srow += 16;
+        if (srow == kB2StageSteps) srow = 0;
+        posS += 16;
+        if (posS == M) {
+            posS = 0;
+            idxT = idxL;
+            kT = kL;
+            gL++;
+            if (++kL == K) kL = 0;
+        }
+        if (++a == TA) {
+            a = 0;
+            idxL++;
+        }
+    }
+    __syncwarp();
+    drain_ready(NBLK * 16);
+    (void)idxT;
+}
+
+}  // namespace b200dp

@@ -8,7 +8,9 @@
 //                  belongs to strip k = (i-1)/32, lane t = (i-1)%32 and is touched at
 //                  wavefront step sigma = (j-1) + t of that strip:
 //                    elem(b,i,j,s) = b*pair_stride + k*strip_stride + sigma*96 + s*32 + t
-//                    strip_stride = (M+31)*96, pair_stride = ceil(N/32)*strip_stride.
+//                    strip_stride = M*96, pair_stride = ceil(N/32)*strip_stride + 31*96
+//                  (chained-dense: the 31 ramp steps of consecutive strips interleave
+//                  lane-wise, no step of a pair's storage is padding).
 //                  One step of a strip is 384 contiguous bytes (3 states x 32 lanes) and
 //                  consecutive steps are contiguous, so the forward streams Q out
 //                  sequentially and the backward streams it back in with 1-D bulk TMA.
@@ -103,6 +105,12 @@ __device__ __forceinline__ void tma_bulk_load(void* dst, const void* src, uint32
             smem_u32(dst)),
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+// L2 prefetch of a tensor-map box (no shared-memory destination, no completion)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(c2)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -243,7 +251,7 @@ __device__ __forceinline__ int progress_wait(const unsigned long long* word, uns
 
 struct QLayout {
     long long pair_stride;    // floats per pair  = K * strip_stride
-    long long strip_stride;   // floats per strip = (M + 31) * 96
+    long long strip_stride;   // floats per strip = M * 96 (consecutive strips overlap by 31 ramp steps)
     int K;                    // strips per pair  = ceil(N / 32)
 };
 

@@ -23,6 +23,8 @@ struct FwdParams {
     QLayout ql;
     int i0;               // 1 = Needleman-Wunsch, 2 = "Smith-Waterman" (sw.py:54-55)
     int flags;
+    int pf_tiles;         // softdp_fwd3: L2 prefetch box width in 16-column tiles (0 = off)
+    int pf_dist;          // ... issued this many tiles ahead of the leading TMA tile
 };
 
 constexpr int kFwdWarpBytes = 2 * kRowRing * kTileElems * 4;   // theta ring + A ring

@@ -1,9 +1,19 @@
 // softdp_fwd2.cuh -- forward fill, fast path (reference: deepblast/nw.py:46-62,
 // sw.py:46-62; replaces deepblast/nw_cuda.py:46-79).
 //
-// Same wavefront as softdp_fwd.cuh (lane t owns row 32k+t+1, one column per step,
-// V carried as an fp32 (hi, lo) pair, Q streamed out strip-major, 384 contiguous bytes
-// per step) re-organised for instruction count and occupancy:
+// Same wavefront as softdp_fwd.cuh (lane t owns row 32k+t+1, one column per step, Q
+// streamed out strip-major, 384 contiguous bytes per step) re-organised for instruction
+// count, dependent-chain length and occupancy:
+//   * DIFFERENCE FORM.  V itself is never formed.  Each lane carries v = V[i,j]-V[i-1,j]
+//     and hands h = V[i,j]-V[i,j-1] to the lane below; with a = A[i-1,j-1]
+//         dx = a + h[i-1,j],  dy = a + v[i,j-1],  l = theta + logsumexp(dx, 0, dy)
+//         h[i,j] = l - v[i,j-1],  v[i,j] = l - h[i-1,j]          (nw.py:56-60 rearranged)
+//     h and v stay O(1), so plain fp32 keeps |dQ| ~ 1e-6 at 1024^2 without the (hi, lo)
+//     pairs of the general kernel: one shuffle per step instead of two and a dependent
+//     chain of ~90 instead of ~130 cycles.  Everything is held in log2 units (theta and A
+//     enter through FFMAs with log2 e) so ex2 / lg2 apply directly.
+//     Vt = V[n,m] = ln 2 * sum_j h[n,j], accumulated per lane (block partial sums folded
+//     into a two-float accumulator);
 //   * steps run in blocks of 16; blocks in which every lane is inside the lattice are
 //     fully unrolled with no per-lane predicates ("steady"), the ramps use the
 //     predicated variant of the same step ("edge");
@@ -27,27 +37,28 @@ __host__ __device__ inline size_t fwd2_smem_bytes(int W, int M) {
     b = (b + 15) & ~(size_t)15;
     b += (size_t)(W + 1) * 8;
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)(W + 1) * (size_t)M * 8;
-    b += 512;                                      // 16 zero (hi, lo) pairs + slack for ramp reads
+    b += (size_t)(W + 1) * (size_t)M * 4;
+    b += 256;                                      // 16 zeros (row above a pair) + slack for ramp reads
     return b;
 }
 
-// One wavefront step of one lane.  EDGE adds the lattice-membership predicates and the
-// zero border cells; SWM adds the sw.py i, j >= 2 rule.  All state by reference.
+// One wavefront step of one lane in difference form (log2 units).  EDGE adds the
+// lattice-membership predicates and the zero border cells; SWM adds the sw.py i, j >= 2
+// rule.  hup = h of the row above at this column, v = the lane's own vertical difference
+// at the previous column (in), this column (out); returns h of this cell.
 // DBG (diagnostic builds only): bit 0 = drop the Q stores, bit 1 = no theta/A staging.
 template <bool EDGE, bool SWM, int DBG = 0>
-__device__ __forceinline__ void fwd2_step(float th, float a, float uh, float ul, float& vh, float& vl, float& dh,
-                                          float& dl, float* __restrict__ qp, bool store, bool comp) {
-    // u_x - u_m and u_y - u_m (nw.py:56-58) from the (hi, lo) pairs
-    const float dx = ((uh - dh) + (ul - dl)) + a;
-    const float dy = ((vh - dh) + (vl - dl)) + a;
+__device__ __forceinline__ float fwd2_step(float th, float a, float hup, float& v, float* __restrict__ qp,
+                                           bool store, bool comp) {
+    const float dx = fmaf(a, kLog2e, hup);           // u_x - u_m   (nw.py:56-58), log2 units
+    const float dy = fmaf(a, kLog2e, v);             // u_y - u_m
     // softmax / logsumexp over (dx, 0, dy), nw.py:10-27.  Relative to the maximum the
     // largest term is exactly 1, so only two exponentials are evaluated (XU pipe), and
     // 1/S with S in [1, 3] runs on the FMA pipe.
     const float hi = fmaxf(dx, dy), lo = fminf(dx, dy);
     const float mx = fmaxf(hi, 0.f);
-    const float e1 = fast_ex2(-fabsf(hi) * kLog2e);          // the smaller of exp(hi - mx), exp(0 - mx)
-    const float e2 = fast_ex2((lo - mx) * kLog2e);
+    const float e1 = fast_ex2(-fabsf(hi));           // the smaller of 2^(hi - mx), 2^(0 - mx)
+    const float e2 = fast_ex2(lo - mx);
     const float S = (1.f + e1) + e2;
     const float r = rcp_1to3(S);
     const float e1r = e1 * r, e2r = e2 * r;
@@ -56,16 +67,15 @@ __device__ __forceinline__ void fwd2_step(float th, float a, float uh, float ul,
     float qm = hi_pos ? e1r : r;
     float qx = x_is_hi ? qhi : e2r;
     float qy = x_is_hi ? e2r : qhi;
-    // V[i,j] = V[i-1,j-1] + (theta + logsumexp(dx, 0, dy))   (nw.py:59-60), Fast2Sum
-    const float delta = th + fmaf(fast_lg2(S), kLn2, mx);
-    const float t1 = delta + dl;
-    float nh = dh + t1;
-    float nl = t1 - (nh - dh);
+    // l = theta + logsumexp = V[i,j] - V[i-1,j-1]   (nw.py:59-60)
+    const float l = fast_lg2(S) + fmaf(th, kLog2e, mx);
+    float hn = l - v;
+    float vn = l - hup;
     if (EDGE || SWM) {
-        // outside the lattice (or below the sw.py origin) V is 0; Q there is only stored
-        // (as zeros) for sw.py's first row / column
-        nh = comp ? nh : 0.f;
-        nl = comp ? nl : 0.f;
+        // outside the lattice (or below the sw.py origin) V is 0, so are its differences;
+        // Q there is only stored (as zeros) for sw.py's first row / column
+        hn = comp ? hn : 0.f;
+        vn = comp ? vn : 0.f;
         if (SWM) {
             qx = comp ? qx : 0.f;
             qm = comp ? qm : 0.f;
@@ -79,10 +89,8 @@ __device__ __forceinline__ void fwd2_step(float th, float a, float uh, float ul,
         qp[32] = qm;
         qp[64] = qy;
     }
-    dh = uh;
-    dl = ul;
-    vh = nh;
-    vl = nl;
+    v = vn;
+    return hn;
 }
 
 template <bool SWM, int RING, int DBG = 0>
@@ -104,7 +112,7 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
     unsigned long long* prog = reinterpret_cast<unsigned long long*>(smem_raw + off);
     off += (size_t)NB * 8;
     off = (off + 15) & ~(size_t)15;
-    float2* bnd = reinterpret_cast<float2*>(smem_raw + off);
+    float* bnd = reinterpret_cast<float*>(smem_raw + off);
 
     if (t == 0) {
         for (int s = 0; s < kF2Ring; ++s) mbar_init(&bars[s], 1);
@@ -119,9 +127,9 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
 
     // lane-constant part of the tile address: group, row, and the -4*tp column skew
     const int lanebase = g * 2048 + tp * 60;
-    // 16 zero (hi, lo) pairs: the "row above" of a pair's first strip
-    float2* zero_row = bnd + (size_t)NB * Mcap;
-    if (threadIdx.x < 16) zero_row[threadIdx.x] = make_float2(0.f, 0.f);
+    // 16 zeros: h of the "row above" of a pair's first strip (V[0, .] = 0)
+    float* zero_row = bnd + (size_t)NB * Mcap;
+    if (threadIdx.x < 16) zero_row[threadIdx.x] = 0.f;
     __syncthreads();
 
     Strip cur, nxt;
@@ -163,15 +171,16 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
         const bool has_up = k > 0;
         const bool feeds_down = (k + 1 < cur.K);
         const unsigned q = cur.q;
-        const float2* bnd_r = bnd + (size_t)((q + NB - 1) % NB) * Mcap;
-        float2* bnd_w = bnd + (size_t)(q % NB) * Mcap;
+        const float* bnd_r = bnd + (size_t)((q + NB - 1) % NB) * Mcap;
+        float* bnd_w = bnd + (size_t)(q % NB) * Mcap;
         const unsigned long long* prog_r = prog + ((q + NB - 1) % NB);
         unsigned long long* prog_w = prog + (q % NB);
 
-        float vh = 0.f, vl = 0.f, dh = 0.f, dl = 0.f;
+        float v = 0.f, h = 0.f;                       // differences, log2 units
+        float acc_hi = 0.f, acc_lo = 0.f;             // sum_j h[i, j] of the lane's row
         // cell (i, j = c+1), c = s' - t, is wavefront step sigma = s' of strip k
         float* qp = p.Q + (long long)cur.pair * p.ql.pair_stride + (long long)k * p.ql.strip_stride + t;
-        float2* bw31 = bnd_w - 31;
+        float* bw31 = bnd_w - 31;
 
         int avail = 0;
         unsigned slotA = 0, slotB = 0;
@@ -196,57 +205,66 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
             const float* baseA = reinterpret_cast<const float*>(ring + slotA * kF2SlotBytes + lanebase + 64);
             const float* baseB = reinterpret_cast<const float*>(ring + slotB * kF2SlotBytes + lanebase);
             const bool steady = full_rows && b >= 2 && s0 + 16 <= m && !(SWM && k == 0);
+            float part = 0.f;
             if (steady) {
-                const float2* br = has_up ? bnd_r + s0 : zero_row;
-                float2* bw = bw31 + s0;
-                // stage the block's operands in registers up front: 16 theta, 16 A and the
-                // 16 boundary pairs (uniform address, broadcast) -- one shared-memory
-                // latency per block instead of one per step on the dependent chain
-                float th_[16], a_[16];
-                float2 bv_[16];
+                const float* br = has_up ? bnd_r + s0 : zero_row;
+                float* bw = bw31 + s0;
+                // stage the block's operands in registers up front: 16 theta, 16 A and the 16 boundary
+                // values (uniform address, broadcast) -- one shared-memory latency per block
+                // instead of one per step on the dependent chain
+                float th_[16], a_[16], bv_[16];
 #pragma unroll
                 for (int ss = 0; ss < 16; ++ss) {
                     const float* tb = (tp <= ss) ? baseB : baseA;
                     th_[ss] = tb[ss];
                     a_[ss] = tb[ss + 256];
-                    bv_[ss] = br[ss];
+                }
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 b4 = reinterpret_cast<const float4*>(br)[q4];
+                    bv_[4 * q4] = b4.x;
+                    bv_[4 * q4 + 1] = b4.y;
+                    bv_[4 * q4 + 2] = b4.z;
+                    bv_[4 * q4 + 3] = b4.w;
                 }
 #pragma unroll
                 for (int ss = 0; ss < 16; ++ss) {
-                    float uh = __shfl_up_sync(kFull, vh, 1);
-                    float ul = __shfl_up_sync(kFull, vl, 1);
-                    uh = (t == 0) ? bv_[ss].x : uh;
-                    ul = (t == 0) ? bv_[ss].y : ul;
-                    fwd2_step<false, false, DBG>(th_[ss], a_[ss], uh, ul, vh, vl, dh, dl, qp + ss * kStepFloats, true,
-                                                 true);
-                    if (t == 31 && feeds_down) bw[ss] = make_float2(vh, vl);
+                    float hup = __shfl_up_sync(kFull, h, 1);
+                    hup = (t == 0) ? bv_[ss] : hup;
+                    h = fwd2_step<false, false, DBG>(th_[ss], a_[ss], hup, v, qp + ss * kStepFloats, true, true);
+                    part += h;
+                    if (t == 31 && feeds_down) bw[ss] = h;
                 }
                 qp += 16 * kStepFloats;
             } else {
                 // ramp blocks: the steady step with the lattice-membership selects
                 const bool cap = (k + 1 == cur.K) && (((m - 1 + ((n - 1) & 31)) >> 4) == b);
-                const float2* br = has_up ? bnd_r + s0 : zero_row;
+                const float* br = has_up ? bnd_r + s0 : zero_row;
                 const int brlim = has_up ? m - s0 : 16;      // entries of br that exist
 #pragma unroll 4
                 for (int ss = 0; ss < 16; ++ss) {
                     const int c = s0 + ss - t;
-                    float uh = __shfl_up_sync(kFull, vh, 1);
-                    float ul = __shfl_up_sync(kFull, vl, 1);
-                    if (t == 0) {
-                        const float2 bv = br[ss < brlim ? ss : 0];
-                        uh = bv.x;
-                        ul = bv.y;
-                    }
+                    float hup = __shfl_up_sync(kFull, h, 1);
+                    if (t == 0) hup = br[ss < brlim ? ss : 0];
                     const bool in = row_ok && (unsigned)c < (unsigned)m;
                     const bool comp = SWM ? (in && rowcomp && (c + 1) >= 2) : in;
                     const float* tb = (tp <= ss) ? baseB : baseA;
                     const float th = tb[ss];
                     const float a = tb[ss + 256];
-                    fwd2_step<true, SWM, DBG>(th, a, uh, ul, vh, vl, dh, dl, qp, in, comp);
-                    if (t == 31 && feeds_down && in) bnd_w[c] = make_float2(vh, vl);
-                    if (cap && in && i == n && c == m - 1) p.Vt[cur.pair] = vh + vl;
+                    h = fwd2_step<true, SWM, DBG>(th, a, hup, v, qp, in, comp);
+                    part += h;
+                    if (t == 31 && feeds_down && in) bnd_w[c] = h;
+                    // Vt = V[n, m] = ln 2 * sum_j h[n, j]
+                    if (cap && in && i == n && c == m - 1) p.Vt[cur.pair] = (acc_hi + (acc_lo + part)) * kLn2;
                     qp += kStepFloats;
                 }
+            }
+            {
+                // fold the block's partial row sum into the two-float accumulator (Fast2Sum)
+                const float t1 = part + acc_lo;
+                const float nh = acc_hi + t1;
+                acc_lo = t1 - (nh - acc_hi);
+                acc_hi = nh;
             }
             if (W > 1 && feeds_down && t == 31) {
                 const int done = min(max(s0 + 16 - 31, 0), m);

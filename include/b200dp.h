@@ -20,7 +20,7 @@
  *                  s lives at
  *                    b*pair_stride + k*strip_stride + ((j-1) + t)*96 + s*32 + t,
  *                    k = (i-1)/32, t = (i-1)%32,
- *                  with strip_stride = (M+31)*96, pair_stride = ceil(N/32)*strip_stride
+ *                  with strip_stride = M*96, pair_stride = ceil(N/32)*strip_stride + 31*96
  *                  (b200dp_q_layout()).  Border cells are implicit (zeros, and
  *                  Q[N+1,M+1,:] = 1) and not stored.  The pointer passed is the storage
  *                  base (16-byte aligned); the allocation must be B*pair_stride + pad

@@ -84,15 +84,52 @@ SPECS_V1 = [
 ]
 
 
+# chained kernels (softdp_fwd3 / softdp_bwd3): forced on small batches through the env
+SPECS_V3 = [
+    ("fwd_v3_n1_64", "nw", 3, 64, 64, 0, 0, 0),
+    ("all_v3_n1_grid", "nw", 13, 96, 128, 0, 0, 3),
+    ("all_v3_n2_256", "nw", 5, 256, 256, 0, 0, 0),
+    ("all_v3_n2_odd", "nw", 7, 160, 112, 0, 0, 2),
+    ("all_v3_n2_ragN", "nw", 4, 100, 96, 0, 0, 0),
+    ("all_v3_n1_ragN", "sw", 4, 77, 80, 0, 0, 3),
+    ("all_v3_n1_sw", "sw", 6, 128, 64, 0, 0, 4),
+    ("all_v3_n2_sw", "sw", 6, 192, 160, 0, 0, 4),
+    ("all_v3_n2_r6", "nw", 9, 128, 256, 0, 0, 2),
+    ("all_v3_dflt_300", "nw", 300, 64, 64, 0, 0, 0),
+    ("all_v3_n2_1024", "nw", 2, 1024, 1024, 0, 0, 0),
+]
+ENVS = {
+    "fwd_v3_n1_64": {"B200DP_NCH": "1"},
+    "all_v3_n1_grid": {"B200DP_NCH": "1", "B200DP_RING": "4", "B200DP_BRING": "2", "B200DP_PFW": "64"},
+    "all_v3_n2_256": {"B200DP_NCH": "2"},
+    "all_v3_n2_odd": {"B200DP_NCH": "2", "B200DP_RING": "3"},
+    "all_v3_n2_ragN": {"B200DP_NCH": "2"},
+    "all_v3_n1_ragN": {"B200DP_NCH": "1"},
+    "all_v3_n1_sw": {"B200DP_NCH": "1"},
+    "all_v3_n2_sw": {"B200DP_NCH": "2"},
+    "all_v3_n2_r6": {"B200DP_NCH": "2", "B200DP_RING": "6", "B200DP_BRING": "6", "B200DP_PFW": "128", "B200DP_PFD": "12"},
+    "all_v3_dflt_300": {},
+    "all_v3_n2_1024": {"B200DP_NCH": "2"},
+}
+
+
 def main():
     want = sys.argv[1:]
-    for spec in SPECS + SPECS_V1:
+    for spec in SPECS_V3 + SPECS + SPECS_V1:
         if want and not any(w in spec[0] for w in want):
             continue
         code = CHECK % dict(root=ROOT, spec=spec)
         t0 = time.time()
         try:
-            p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=90)
+            env = dict(os.environ)
+            if spec[0] in ENVS:
+                env["B200DP_V3MIN"] = "1"
+                env.update(ENVS[spec[0]])
+                if spec[0] == "all_v3_dflt_300":
+                    env.pop("B200DP_V3MIN")
+            else:
+                env["B200DP_V3"] = "0"
+            p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=90, env=env)
             out = (p.stdout.strip().splitlines() or ["(no stdout)"])[-1]
             if p.returncode != 0:
                 out = "ERROR rc=%d %s | %s" % (p.returncode, out, p.stderr.strip().splitlines()[-1:] )

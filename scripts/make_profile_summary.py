@@ -28,9 +28,11 @@ with open(os.path.join(P, f"{tag}_launches_{wl}.csv"), "w") as f:
     for k, d in launches:
         f.write('"%s",%d\n' % (k.replace('"', "'"), d))
 ours = [(k, d) for k, d in launches if "softdp" in k]
-tot = sum(d for _, d in launches[3:]) or 1.0      # skip the input-generation kernels
+# the step's own launches: skip input generation and the untimed spin kernel bench.py queues
+steps = [(k, d) for k, d in launches if not any(x in k for x in ("distribution_elementwise", "neg_kernel", "spin_kernel"))]
+tot = sum(d for _, d in steps) or 1.0
 share = {}
-for k, d in launches[3:]:
+for k, d in steps:
     key = "softdp_fwd" if "softdp_fwd" in k else "softdp_bwd" if "softdp_bwd" in k else "other (torch sum/fill)"
     share[key] = share.get(key, 0.0) + d
 # ---- full capture -----------------------------------------------------------------------

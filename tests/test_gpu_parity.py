@@ -204,6 +204,67 @@ def test_full_size_properties(ops, mode):
     np.testing.assert_allclose(E[idx].cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
 
 
+CHAINED = [
+    # mode, B, N, M, chains per warp, CTAs (0 = one per pair), ring slots (fwd, bwd)
+    ("nw", 3, 64, 64, 1, 0, 3, 3),
+    ("nw", 13, 96, 128, 1, 3, 4, 2),        # several pairs per CTA, boustrophedon dealing
+    ("nw", 5, 256, 256, 2, 0, 3, 3),
+    ("nw", 7, 160, 112, 2, 2, 3, 3),        # odd strip count: a dead chain in the last pass
+    ("nw", 4, 100, 96, 2, 0, 3, 3),         # N % 32 != 0
+    ("sw", 4, 77, 80, 1, 3, 3, 3),
+    ("sw", 6, 128, 64, 1, 4, 6, 4),
+    ("sw", 6, 192, 160, 2, 4, 8, 6),
+    ("nw", 2, 1024, 1024, 2, 0, 6, 3),
+    ("nw", 2, 512, 1024, 1, 1, 3, 3),
+]
+
+
+@pytest.mark.parametrize("mode,B,N,M,nch,ctas,ring,bring", CHAINED)
+def test_chained_kernels_vs_oracle(ops, monkeypatch, mode, B, N, M, nch, ctas, ring, bring):
+    """softdp_fwd3 / softdp_bwd3 (the large-batch path) forced onto small batches."""
+    monkeypatch.setenv("B200DP_V3MIN", "1")
+    monkeypatch.setenv("B200DP_NCH", str(nch))
+    monkeypatch.setenv("B200DP_RING", str(ring))
+    monkeypatch.setenv("B200DP_BRING", str(bring))
+    if ctas:
+        monkeypatch.setenv("B200DP_CTAS", str(ctas))
+    theta, A = rand_inputs(B, N, M, seed=7)
+    check_fwd_bwd(ops, theta, A, torch.linspace(0.5, 1.5, B), mode, 0)
+
+
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+def test_baseline_batch_1024(ops, mode):
+    """BASELINE configs[1]/[2] at full size (1024 pairs of 256x256: the chained kernels by
+    default dispatch): size-independent properties over the whole batch, the oracle on a
+    subsample, and the same results from the hand-off kernels on the same inputs."""
+    B, N, M = 1024, 256, 256
+    g = torch.Generator(device=dev()).manual_seed(2)
+    th = torch.rand(B, N, M, generator=g, device=dev())
+    a = -torch.rand(B, N, M, generator=g, device=dev())
+    Vt, Q = ops.forward_pass(th, a, mode)
+    Et = torch.ones(B, device=dev())
+    E = ops.backward_pass(Et, Q, mode, N=N)
+    lo = 1 if mode == "sw" else 0
+    Qi = Q.reshape(B, -1, M, 3)[:, :N]                       # [B, N, M, 3] view of the strip-major storage
+    s = Qi[:, lo:, lo:].sum(-1)
+    assert torch.allclose(s, torch.ones_like(s), atol=1e-5)
+    assert torch.isfinite(Vt).all() and torch.allclose(E[:, N, M], Et)
+    assert (E >= 0).all() and float(E.max()) <= 1.0 + 1e-4
+    assert float(E[:, 0].abs().max()) == 0.0 and float(E[:, :, 0].abs().max()) == 0.0
+    assert float(E[:, N + 1, :M + 1].abs().max()) == 0.0 and float(E[:, :N + 1, M + 1].abs().max()) == 0.0
+    idx = [0, 1, 511, 777, 1023]
+    Vt_o, Q_o = O.forward_pass(th[idx].cpu().numpy(), a[idx].cpu().numpy(), mode)
+    E_o = O.backward_pass(np.ones(len(idx), np.float32), Q_o, mode)
+    np.testing.assert_allclose(Vt[idx].cpu().numpy(), Vt_o, rtol=1e-6)
+    np.testing.assert_allclose(Qi[idx].cpu().numpy(), interior(Q_o), rtol=0, atol=ATOL_QE)
+    np.testing.assert_allclose(E[idx].cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
+    # the 8-warps-per-pair hand-off kernels compute the same cells with the same arithmetic
+    Vt2, Q2 = ops.forward_pass(th[:64], a[:64], mode, flags=8 << 4)
+    E2 = ops.backward_pass(Et[:64], Q2, mode, flags=8 << 4, N=N)
+    assert torch.allclose(Q2.reshape(64, -1, M, 3)[:, :N], Qi[:64], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(E2.cpu().numpy(), E[:64].cpu().numpy(), rtol=0, atol=1e-6)
+
+
 def test_large_lattice_1024(ops):
     """fp32 alone fails the 1e-4 bar here; the (hi, lo) carry must not."""
     B, N, M = 1, 1024, 1024

@@ -30,7 +30,7 @@ def test_q_layout_is_a_valid_strided_view():
     from deepblast_b200 import _lib
     for N, M in [(1, 1), (5, 4), (31, 33), (32, 32), (256, 256), (300, 77), (1000, 2047)]:
         K, ss, ps, pad = _lib.q_layout(N, M)
-        assert K == (N + 31) // 32 and ss == (M + 31) * 96 and ps == K * ss and pad >= 16 * 96
+        assert K == (N + 31) // 32 and ss == M * 96 and ps == K * ss + 31 * 96 and pad >= 16 * 96
         # the 5-D view [K, 32, M, 3] with strides (ss, 97, 96, 32) addresses distinct
         # elements inside the pair's storage: cell (i, j, s) -> k*ss + ((j-1)+t)*96 + s*32 + t
         if K * 32 * M <= 40000:
