@@ -37,24 +37,31 @@ __host__ __device__ inline size_t bwd3_smem_bytes(int M) {
 
 // Drain column tile tc of the segment whose first step had staging row `segrow`
 // (= (segment * M) mod 80): element (r, col) was produced at segment step
-// (M-1-col) + (31-r).  lane = column; 8 independent LDS then 8 coalesced stores.
+// (M-1-col) + (31-r), i.e. it sits in staging row (ub - t - r) mod 80 with the warp-uniform
+// ub = segrow + M + 30 - 32 tc (lane t = column 32 tc + t).  One wrap at most, so row r is
+// read from p0 - 32 r (r <= sr0) or p1 - 32 r (r > sr0): compare, select, LDS with an
+// immediate offset, one IMAD.WIDE for the row address, STG -- 5 instructions per row.
+// FULL = all 32 rows of the strip are inside the lattice (no store predicates).
+template <bool FULL>
 __device__ __forceinline__ void bwd3_drain_tile(const float* __restrict__ stage, float* __restrict__ Erow0, int tc,
                                                 int M, int rmax, int pitch, int t, int segrow) {
-    const int col = tc * kTile + t;
-    float* dstp = Erow0 + col + 1;
-    const int sr0 = (segrow + (M - 1 - col) + 31) % kB2StageSteps;
-#pragma unroll 1
-    for (int r0 = 0; r0 < rmax; r0 += 8) {
+    int sr0 = (segrow + M + 30 - tc * kTile) % kB2StageSteps - t;
+    sr0 += (sr0 < 0) ? kB2StageSteps : 0;
+    const float* p0 = stage + sr0 * kB2StagePitch;
+    const float* p1 = p0 + kB2StageFloats;
+    float* dstp = Erow0 + tc * kTile + t + 1;
+#pragma unroll
+    for (int r0 = 0; r0 < kTile; r0 += 8) {
         float v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            int sr = sr0 - (r0 + q);
-            sr += (sr < 0) ? kB2StageSteps : 0;
-            v[q] = stage[sr * kB2StagePitch + r0 + q];
+            const int r = r0 + q;
+            const float* ps = (r > sr0) ? p1 : p0;
+            v[q] = ps[-(kB2StagePitch - 1) * r];
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-            if (r0 + q < rmax) dstp[(long long)(r0 + q) * pitch] = v[q];
+            if (FULL || r0 + q < rmax) dstp[(r0 + q) * pitch] = v[q];
     }
 }
 
@@ -143,8 +150,10 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
             const int pair = pair_of(d_idx);
             const int kb = K - 1 - d_k;
             float* Eb = p.E + (long long)pair * Epair;
-            bwd3_drain_tile(stage, Eb + (long long)(kb * kTile + 1) * (M + 2), d_tc, M, min(kTile, N - kb * kTile),
-                            M + 2, t, d_segrow);
+            float* Er = Eb + (long long)(kb * kTile + 1) * (M + 2);
+            const int rmax = N - kb * kTile;
+            if (rmax >= kTile) bwd3_drain_tile<true>(stage, Er, d_tc, M, kTile, M + 2, t, d_segrow);
+            else bwd3_drain_tile<false>(stage, Er, d_tc, M, rmax, M + 2, t, d_segrow);
             drained++;
             if (--d_tc < 0) {
                 // strip complete: zero borders, E[N+1, M+1] = Et  (nw.py:125-127, 347)

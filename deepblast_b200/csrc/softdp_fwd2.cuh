@@ -52,21 +52,18 @@ __device__ __forceinline__ float fwd2_step(float th, float a, float hup, float& 
                                            bool store, bool comp) {
     const float dx = fmaf(a, kLog2e, hup);           // u_x - u_m   (nw.py:56-58), log2 units
     const float dy = fmaf(a, kLog2e, v);             // u_y - u_m
-    // softmax / logsumexp over (dx, 0, dy), nw.py:10-27.  Relative to the maximum the
-    // largest term is exactly 1, so only two exponentials are evaluated (XU pipe), and
-    // 1/S with S in [1, 3] runs on the FMA pipe.
-    const float hi = fmaxf(dx, dy), lo = fminf(dx, dy);
-    const float mx = fmaxf(hi, 0.f);
-    const float e1 = fast_ex2(-fabsf(hi));           // the smaller of 2^(hi - mx), 2^(0 - mx)
-    const float e2 = fast_ex2(lo - mx);
-    const float S = (1.f + e1) + e2;
-    const float r = rcp_1to3(S);
-    const float e1r = e1 * r, e2r = e2 * r;
-    const bool hi_pos = hi >= 0.f, x_is_hi = dx >= dy;
-    const float qhi = hi_pos ? r : e1r;
-    float qm = hi_pos ? e1r : r;
-    float qx = x_is_hi ? qhi : e2r;
-    float qy = x_is_hi ? e2r : qhi;
+    // softmax / logsumexp over (dx, 0, dy), nw.py:10-27, relative to the maximum (one
+    // FMNMX3): the largest term is ex2(0) = 1 exactly, S is in [1, 3].  Five XU operations
+    // (3 ex2, rcp, lg2) and 15 FMA/ALU-pipe instructions per cell; the XU pipe runs at about
+    // 30 % at the HBM-bound rate, so trading the selects and the Newton reciprocal of the
+    // earlier two-exponential form for two more XU operations is a net win in issue slots.
+    const float mx = fmaxf(fmaxf(dx, dy), 0.f);
+    const float em = fast_ex2(-mx);
+    const float ex = fast_ex2(dx - mx);
+    const float ey = fast_ex2(dy - mx);
+    const float S = (em + ex) + ey;
+    const float r = fast_rcp(S);
+    float qx = ex * r, qm = em * r, qy = ey * r;
     // l = theta + logsumexp = V[i,j] - V[i-1,j-1]   (nw.py:59-60)
     const float l = fast_lg2(S) + fmaf(th, kLog2e, mx);
     float hn = l - v;
