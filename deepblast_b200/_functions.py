@@ -100,6 +100,11 @@ def make_classes(mode, prefix):
                 v_grad, _ = torch.autograd.grad(v, (theta, A), create_graph=True)
             return v_grad
 
+        def decode_host(self, theta_h, A_h, **kw):
+            """`decode` for HOST tensors: (Vt, dVt/dtheta) as pinned host tensors, with the
+            PCIe copies of consecutive chunks overlapped with the sweeps (ops.decode_host)."""
+            return ops.decode_host(theta_h, A_h, mode, **kw)
+
     for cls, suffix in ((FunctionBackward, "FunctionBackward"), (Function, "Function"),
                         (Decoder, "Decoder")):
         cls.__name__ = prefix + suffix

@@ -634,3 +634,148 @@ int b200dp_traceback(const float* grad, long long sb, long long si, long long sj
 }
 
 }  // extern "C"
+
+// ---- host-buffer entry point: chunked H2D -> fwd -> bwd -> D2H pipeline ---------------------
+//
+// What a caller holding theta / A in HOST memory pays for NeedlemanWunschDecoder.decode
+// (deepblast/nw_cuda.py:319-325: forward, then autograd.grad of sum(Vt)) is dominated by
+// the PCIe copies (8 B/cell in, 4 B/cell out), not by the kernels.  The batch is cut into
+// chunks that flow through three workspace slots on three internal streams, so that the
+// upload of chunk c+1, the two sweeps of chunk c and the download of chunk c-1 overlap
+// (PCIe is full duplex): the call costs about max(H2D, D2H) instead of their sum.
+namespace {
+
+struct HostPipe {
+    bool ready = false;
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t in_done[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t cmp_done[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t out_done[3] = {nullptr, nullptr, nullptr};
+};
+std::mutex g_pipe_mu;
+HostPipe g_pipes[64];
+
+__global__ void fill_one_kernel(float* p) { p[0] = 1.0f; }
+
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct HostSlotLayout {
+    size_t theta, A, Q, E, Vt, Et, bytes;
+};
+HostSlotLayout host_slot_layout(int N, int M, int cp) {
+    const QLayout ql = q_layout(N, M);
+    HostSlotLayout L;
+    size_t off = 0;
+    L.theta = off; off = align256(off + (size_t)cp * N * M * 4);
+    L.A = off;     off = align256(off + (size_t)cp * N * M * 4);
+    L.Q = off;     off = align256(off + ((size_t)cp * ql.pair_stride + (size_t)kDiagRows * kStepFloats) * 4);
+    L.E = off;     off = align256(off + (size_t)cp * (N + 2) * (M + 2) * 4);
+    L.Vt = off;    off = align256(off + (size_t)cp * 4);
+    L.Et = off;    off = align256(off + (size_t)cp * 4);
+    L.bytes = off;
+    return L;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t b200dp_decode_host_workspace(int N, int M, int chunk_pairs) {
+    if (N < 1 || M < 1 || chunk_pairs < 1) return 0;
+    return 3 * host_slot_layout(N, M, chunk_pairs).bytes + 256;
+}
+
+int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h, float* Vt_h, float* E_h, int B,
+                       int N, int M, int mode, int chunk_pairs, void* workspace, size_t workspace_bytes, int flags,
+                       void* stream) {
+    if (int rc = check_common("b200dp_decode_host", B, N, M)) return rc;
+    if (mode != B200DP_MODE_NW && mode != B200DP_MODE_SW) return fail(-1, "b200dp_decode_host: bad mode");
+    if (B == 0) return 0;
+    if (!theta_h || !A_h || !Vt_h || !E_h || !workspace) return fail(-1, "b200dp_decode_host: null pointer");
+    if (chunk_pairs < 1) return fail(-1, "b200dp_decode_host: chunk_pairs < 1");
+    if (!aligned(workspace, 256)) return fail(-1, "b200dp_decode_host: workspace must be 256-byte aligned");
+    if (workspace_bytes < b200dp_decode_host_workspace(N, M, chunk_pairs))
+        return fail(-1, "b200dp_decode_host: workspace too small (see b200dp_decode_host_workspace)");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(-2, "b200dp_decode_host: no device");
+    std::lock_guard<std::mutex> lk(g_pipe_mu);      // one pipeline per device, enqueued by one thread at a time
+    HostPipe& hp = g_pipes[dev];
+    if (!hp.ready) {
+        cudaError_t e = cudaSuccess;
+        auto mk = [&](cudaEvent_t* ev) { if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming); };
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp.s_cmp, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking);
+        mk(&hp.fork);
+        mk(&hp.join);
+        for (int i = 0; i < 3; ++i) {
+            mk(&hp.in_done[i]);
+            mk(&hp.cmp_done[i]);
+            mk(&hp.out_done[i]);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "b200dp_decode_host: stream/event creation");
+        hp.ready = true;
+    }
+    cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+    const HostSlotLayout L = host_slot_layout(N, M, chunk_pairs);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    float* one = reinterpret_cast<float*>(ws + 3 * L.bytes);
+    const size_t pairTA = (size_t)N * M, pairE = (size_t)(N + 2) * (M + 2);
+#define B200DP_CK(call, what)                                      \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(e_, what);         \
+    } while (0)
+    // fork: everything below is ordered after the work already queued on the caller's stream
+    B200DP_CK(cudaEventRecord(hp.fork, user), "b200dp_decode_host: fork");
+    B200DP_CK(cudaStreamWaitEvent(hp.s_in, hp.fork, 0), "b200dp_decode_host: fork");
+    B200DP_CK(cudaStreamWaitEvent(hp.s_cmp, hp.fork, 0), "b200dp_decode_host: fork");
+    B200DP_CK(cudaStreamWaitEvent(hp.s_out, hp.fork, 0), "b200dp_decode_host: fork");
+    if (!Et_h) fill_one_kernel<<<1, 1, 0, hp.s_cmp>>>(one);
+    int c = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk_pairs, ++c) {
+        const int nb = (B - b0 < chunk_pairs) ? (B - b0) : chunk_pairs;
+        const int sl = c % 3;
+        unsigned char* sb = ws + (size_t)sl * L.bytes;
+        float* d_theta = reinterpret_cast<float*>(sb + L.theta);
+        float* d_A = reinterpret_cast<float*>(sb + L.A);
+        float* d_Q = reinterpret_cast<float*>(sb + L.Q);
+        float* d_E = reinterpret_cast<float*>(sb + L.E);
+        float* d_Vt = reinterpret_cast<float*>(sb + L.Vt);
+        float* d_Et = reinterpret_cast<float*>(sb + L.Et);
+        // upload: the slot's theta / A are free once the sweeps of chunk c-3 have run
+        B200DP_CK(cudaStreamWaitEvent(hp.s_in, hp.cmp_done[sl], 0), "b200dp_decode_host: wait");
+        B200DP_CK(cudaMemcpyAsync(d_theta, theta_h + (size_t)b0 * pairTA, (size_t)nb * pairTA * 4,
+                                  cudaMemcpyHostToDevice, hp.s_in), "b200dp_decode_host: H2D theta");
+        B200DP_CK(cudaMemcpyAsync(d_A, A_h + (size_t)b0 * pairTA, (size_t)nb * pairTA * 4, cudaMemcpyHostToDevice,
+                                  hp.s_in), "b200dp_decode_host: H2D A");
+        if (Et_h)
+            B200DP_CK(cudaMemcpyAsync(d_Et, Et_h + b0, (size_t)nb * 4, cudaMemcpyHostToDevice, hp.s_in),
+                      "b200dp_decode_host: H2D Et");
+        B200DP_CK(cudaEventRecord(hp.in_done[sl], hp.s_in), "b200dp_decode_host: record");
+        // sweeps: E / Vt of the slot are free once chunk c-3 has been downloaded
+        B200DP_CK(cudaStreamWaitEvent(hp.s_cmp, hp.in_done[sl], 0), "b200dp_decode_host: wait");
+        B200DP_CK(cudaStreamWaitEvent(hp.s_cmp, hp.out_done[sl], 0), "b200dp_decode_host: wait");
+        if (int rc = b200dp_fwd(d_theta, d_A, d_Q, d_Vt, nullptr, nullptr, nb, N, M, mode, flags, hp.s_cmp)) return rc;
+        if (int rc = b200dp_bwd(Et_h ? d_Et : one, Et_h ? 1 : 0, d_Q, d_E, nullptr, nullptr, nb, N, M, mode, flags,
+                                hp.s_cmp))
+            return rc;
+        B200DP_CK(cudaEventRecord(hp.cmp_done[sl], hp.s_cmp), "b200dp_decode_host: record");
+        // download
+        B200DP_CK(cudaStreamWaitEvent(hp.s_out, hp.cmp_done[sl], 0), "b200dp_decode_host: wait");
+        B200DP_CK(cudaMemcpyAsync(E_h + (size_t)b0 * pairE, d_E, (size_t)nb * pairE * 4, cudaMemcpyDeviceToHost,
+                                  hp.s_out), "b200dp_decode_host: D2H E");
+        B200DP_CK(cudaMemcpyAsync(Vt_h + b0, d_Vt, (size_t)nb * 4, cudaMemcpyDeviceToHost, hp.s_out),
+                  "b200dp_decode_host: D2H Vt");
+        B200DP_CK(cudaEventRecord(hp.out_done[sl], hp.s_out), "b200dp_decode_host: record");
+    }
+    // join: the caller's stream continues after the last download (s_out runs in order, and
+    // every download waited for its sweeps, which waited for their uploads)
+    B200DP_CK(cudaEventRecord(hp.join, hp.s_out), "b200dp_decode_host: join");
+    B200DP_CK(cudaStreamWaitEvent(user, hp.join, 0), "b200dp_decode_host: join");
+#undef B200DP_CK
+    return 0;
+}
+
+}  // extern "C"

@@ -202,3 +202,59 @@ def traceback_batch(grad, xlen=None, ylen=None, variant="cuda"):
             raise RuntimeError("b200dp_traceback: output capacity exceeded")
         res.append([tuple(int(v) for v in row) for row in out_h[b, :ln_h[b]]])
     return res
+
+
+_host_ws = {}
+
+
+def decode_host(theta_h, A_h, mode="nw", Et_h=None, chunk_pairs=None, out=None, device=None, flags=0):
+    """Host-buffer form of `Decoder.decode` (nw_cuda.py:319-325): theta_h, A_h [B,N,M] fp32
+    HOST tensors (pinned for full PCIe speed) -> (Vt_h [B], grad_h [B,N,M]) pinned host
+    tensors, grad_h = dVt/dtheta being a view of the padded E the engine downloads.
+    Uploads, sweeps and downloads of consecutive chunks overlap (b200dp_decode_host).
+    Returns after the results have landed unless `out` is given with sync=False semantics
+    handled by the caller (see `decode_host_async`)."""
+    Vt_h, E_h = decode_host_async(theta_h, A_h, mode, Et_h, chunk_pairs, out, device, flags)
+    torch.cuda.current_stream(device).synchronize()
+    return Vt_h, E_h[:, 1:-1, 1:-1]
+
+
+def decode_host_async(theta_h, A_h, mode="nw", Et_h=None, chunk_pairs=None, out=None, device=None, flags=0):
+    """Enqueue only; returns (Vt_h, E_h padded [B,N+2,M+2]) pinned buffers that are valid
+    after the current stream of `device` has been synchronised."""
+    for name, t in (("theta_h", theta_h), ("A_h", A_h)):
+        if t.is_cuda:
+            raise RuntimeError(f"{name} must be a host tensor (use Decoder.decode for CUDA tensors)")
+        if t.dtype != torch.float32:
+            raise TypeError("CUDA variant only supports torch.float32 type")
+    if tuple(A_h.shape) != tuple(theta_h.shape) or theta_h.dim() != 3:
+        raise RuntimeError("theta_h and A_h must both be [B, N, M]")
+    if not torch.cuda.is_available():
+        raise RuntimeError("deepblast_b200 needs a CUDA device: there is no CPU path")
+    B, N, M = theta_h.shape
+    theta_h = theta_h.contiguous()
+    A_h = A_h.contiguous()
+    if Et_h is not None:
+        Et_h = Et_h.contiguous().float()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if chunk_pairs is None:
+        # enough chunks to hide the first upload and the last download, each still a few MB
+        chunk_pairs = max(1, min(B, max(8, (4 << 20) // max(1, N * M)), (B + 11) // 12 if B >= 24 else B))
+    with torch.cuda.device(dev):
+        need = _lib.lib().b200dp_decode_host_workspace(N, M, chunk_pairs)
+        key = (dev.index, N, M, chunk_pairs)
+        ws = _host_ws.get(key)
+        if ws is None or ws.numel() < need:
+            _host_ws.clear()                       # one cached workspace per process is enough
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            _host_ws[key] = ws
+        if out is None:
+            Vt_h = torch.empty(B, dtype=torch.float32, pin_memory=True)
+            E_h = torch.empty((B, N + 2, M + 2), dtype=torch.float32, pin_memory=True)
+        else:
+            Vt_h, E_h = out
+        rc = _lib.lib().b200dp_decode_host(theta_h.data_ptr(), A_h.data_ptr(), _ptr(Et_h), Vt_h.data_ptr(),
+                                           E_h.data_ptr(), B, N, M, MODES[mode], chunk_pairs, ws.data_ptr(),
+                                           ws.numel(), flags, torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "b200dp_decode_host")
+    return Vt_h, E_h

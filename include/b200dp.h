@@ -36,6 +36,7 @@
 #ifndef B200DP_H
 #define B200DP_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -96,6 +97,20 @@ int b200dp_adj_bwd(const float* E, const float* Q, const float* Qd, float* Ed,
 int b200dp_traceback(const float* grad, long long sb, long long si, long long sj,
                      const int32_t* xlen, const int32_t* ylen, int B, int N, int M,
                      int variant, int32_t* out, int cap, int32_t* len, void* stream);
+
+/* Host-buffer form of NeedlemanWunschDecoder.decode (deepblast/nw_cuda.py:319-325: forward,
+ * then autograd.grad of sum(Vt), i.e. _forward_pass_kernel + _backward_pass_kernel) for a
+ * caller whose theta / A live in HOST memory (pinned for full PCIe speed):
+ *   theta_h, A_h [B, N, M], Et_h [B] or NULL (= ones, what sum(Vt).backward() feeds)
+ *   -> Vt_h [B], E_h [B, N+2, M+2] (padded as the reference's E; dVt/dtheta = E[:, 1:-1, 1:-1]).
+ * The batch is cut into chunks of chunk_pairs that flow upload -> fwd -> bwd -> download
+ * through three slots of the caller-provided DEVICE workspace on three internal streams, so
+ * uploads, sweeps and downloads overlap.  Asynchronous: forked from `stream` and joined back
+ * into it; the host buffers are valid once the caller has synchronised `stream`. */
+size_t b200dp_decode_host_workspace(int N, int M, int chunk_pairs);
+int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h, float* Vt_h,
+                       float* E_h, int B, int N, int M, int mode, int chunk_pairs,
+                       void* workspace, size_t workspace_bytes, int flags, void* stream);
 
 #ifdef __cplusplus
 }

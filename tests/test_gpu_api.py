@@ -161,3 +161,42 @@ def test_install_patches_reference_names():
     finally:
         for name in ("deepblast", "deepblast.nw_cuda", "deepblast.sw_cuda", "deepblast.alignment"):
             sys.modules.pop(name, None)
+
+
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+@pytest.mark.parametrize("B,N,M,chunk", [(37, 64, 96, 8), (5, 33, 40, 2), (300, 64, 64, None)])
+def test_decode_host_matches_device_path_and_oracle(mode, B, N, M, chunk):
+    """Host-buffer entry (b200dp_decode_host): chunked upload / sweep / download pipeline
+    gives exactly what the autograd path gives on the same inputs, and matches the oracle."""
+    from deepblast_b200 import ops
+    from oracle import softdp as O
+    g = torch.Generator().manual_seed(7)
+    theta_h = torch.rand(B, N, M, generator=g).pin_memory()
+    A_h = (-torch.rand(B, N, M, generator=g)).pin_memory()
+    for rep in range(2):                      # second call reuses the slots and events
+        Vt_h, g_h = ops.decode_host(theta_h, A_h, mode, chunk_pairs=chunk)
+    dec = decoders()[mode]('softmax')
+    theta = theta_h.to(dev()).requires_grad_()
+    A = A_h.to(dev()).requires_grad_()
+    aln = dec.decode(theta, A)
+    Vt = dec(theta, A)
+    torch.cuda.synchronize()
+    assert torch.equal(g_h, aln.detach().cpu())
+    assert torch.equal(Vt_h, Vt.detach().cpu())
+    nb = min(B, 6)
+    Vt_o, Q_o, E_o = O.decode(theta_h[:nb].numpy(), A_h[:nb].numpy(), mode)
+    np.testing.assert_allclose(g_h[:nb].numpy(), E_o[:, 1:-1, 1:-1], atol=1e-4, rtol=1e-4)
+    np.testing.assert_allclose(Vt_h[:nb].numpy(), Vt_o, rtol=1e-5)
+    # per-pair upstream gradients
+    Et_h = torch.rand(B, generator=g)
+    Vt2, g2 = ops.decode_host(theta_h, A_h, mode, Et_h=Et_h, chunk_pairs=chunk)
+    np.testing.assert_allclose(g2.numpy(), g_h.numpy() * Et_h.numpy()[:, None, None], rtol=2e-6, atol=1e-7)
+
+
+def test_decode_host_rejects_cuda_and_bad_dtype():
+    from deepblast_b200 import ops
+    t = torch.rand(2, 8, 8)
+    with pytest.raises(RuntimeError):
+        ops.decode_host(t.to(dev()), t, "nw")
+    with pytest.raises(TypeError):
+        ops.decode_host(t.double(), t.double(), "nw")
