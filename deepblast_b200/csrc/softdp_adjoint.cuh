@@ -7,7 +7,8 @@
 // Ztheta and E are padded row-major tensors whose row pitch (M+2)*4 B is not a
 // multiple of 16 B, so they cannot be described by a TMA tensor map; their 32x32
 // tiles are staged with 4-byte cp.async on the same mbarriers.  Q and Qd are
-// strip-major and arrive by 1-D bulk TMA, 6 KB per copy.
+// strip-major (two stored states per cell, softdp_common.cuh) and arrive by 1-D bulk TMA,
+// 4 KB per copy.
 #pragma once
 #include "softdp_pipes.cuh"
 
@@ -145,8 +146,9 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(AdjFwdParams p) {
                 const int o = (int)lslot * kTileElems + t * kTile + (c & 31);
                 const float zt = rtiles[o];
                 const float za = rtiles[kRowRing * kTileElems + o];
-                const float* qt = qring + dslot * kDiagElems + (s & (kDiagRows - 1)) * 96 + t;
-                const float qx = qt[0], qm = qt[32], qy = qt[64];
+                const float* qt = qring + dslot * kDiagElems + (s & (kDiagRows - 1)) * kStepFloats + t;
+                const float qx = qt[0], qy = qt[kQY];
+                const float qm = (1.f - qx) - qy;          // the implied state
                 // w_x - w_m, w_y - w_m with w = (za + Vd[i-1,j], Vd[i-1,j-1], za + Vd[i,j-1]) (nw.py:188-192)
                 const float dxm = ((uh - dh) + (ul - dl)) + za;
                 const float dym = ((vh - dh) + (vl - dl)) + za;
@@ -161,12 +163,13 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(AdjFwdParams p) {
                 const float r = fmaf(qx, dxm, qy * dym);
                 // g = tsum - w_m,  tsum = sum_s q_s w_s (nw.py:193-196)
                 const float g = fmaf(eps, dh, fmaf(eps, dl, r));
-                float qdx = qx * (dxm - g), qdm = qm * (-g), qdy = qy * (dym - g);   // nw.py:30-43
-                if (s2 == 0.f) {
-                    // Q[i,j,:] == 0 (first row/column of the sw.py lattice): Vd = Ztheta
+                // nw.py:30-43; qd_m = q_m (-g) = -(qd_x + qd_y) up to rounding and is implied
+                float qdx = qx * (dxm - g), qdy = qy * (dym - g);
+                if (qx < 0.f) {
+                    // marked cell: Q[i,j,:] == 0 (first row/column of the sw.py lattice): Vd = Ztheta
                     nh = zt;
                     nl = 0.f;
-                    qdx = qdm = qdy = 0.f;
+                    qdx = qdy = 0.f;
                 } else {
                     const float delta = zt + g;
                     const float t1 = delta + dl;
@@ -174,8 +177,7 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(AdjFwdParams p) {
                     nl = t1 - (nh - dh);
                 }
                 qdp[0] = qdx;
-                qdp[32] = qdm;
-                qdp[64] = qdy;
+                qdp[kQY] = qdy;
             }
             if (t == 31 && feeds_down && in) {
                 bnd_w[j - 1] = make_float2(nh, nl);
@@ -341,13 +343,19 @@ __global__ void __launch_bounds__(256) softdp_adj_bwd_kernel(AdjBwdParams p) {
             if (in) {
                 const float e = etiles[lslot * kTileElems + t * kTile + (31 - (cr & 31))];
                 const float* qt =
-                    qring + (2 * dslot) * kDiagElems + (kDiagRows - 1 - (s & (kDiagRows - 1))) * 96 + t;
+                    qring + (2 * dslot) * kDiagElems + (kDiagRows - 1 - (s & (kDiagRows - 1))) * kStepFloats + t;
                 const float* qdt = qt + kDiagElems;
                 ed = zin + yprev;
                 // nw.py:260-265, push form
-                X = fmaf(qdt[0], e, qt[0] * ed);
-                D = fmaf(qdt[32], e, qt[32] * ed);
-                Y = fmaf(qdt[64], e, qt[64] * ed);
+                // implied states: q_m = (1 - q_x) - q_y, qd_m = -(qd_x + qd_y);
+                // a marked cell (Q == 0, sw.py first row / column) pushes nothing
+                const float qx = qt[0], qy = qt[kQY];
+                if (qx >= 0.f) {
+                    const float qdx = qdt[0], qdy = qdt[kQY];
+                    X = fmaf(qdx, e, qx * ed);
+                    Y = fmaf(qdy, e, qy * ed);
+                    D = fmaf(-(qdx + qdy), e, ((1.f - qx) - qy) * ed);
+                }
             }
             if (c >= 0 && c < m) otile[((c >> 5) & 1) * kTileElems + t * kTile + (c & 31)] = ed;
             zout = X + dprev;

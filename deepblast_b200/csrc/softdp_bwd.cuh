@@ -6,7 +6,7 @@
 //   X = Q[i,j,x] E[i,j] -> (i-1, j),  D = Q[i,j,m] E[i,j] -> (i-1, j-1),
 //   Y = Q[i,j,y] E[i,j] -> (i, j-1),
 // so every lane multiplies by ITS OWN Q[i,j,:] (strip-major: the sweep reads Q back in
-// exactly the reverse of the order the forward wrote it, 6 KB per 1-D bulk TMA copy)
+// exactly the reverse of the order the forward wrote it, 4 KB per 1-D bulk TMA copy)
 // instead of its successors'.
 // Lane t owns row 32kb+t+1 and walks right to left, lane 31 leading; the value a
 // lane hands upward is Z = X(this step) + D(previous step), one shuffle per step.
@@ -130,12 +130,14 @@ __global__ void __launch_bounds__(256) softdp_bwd_kernel(BwdParams p) {
             const bool comp = in && i >= p.i0 && (c + 1) >= p.i0;
             float e = 0.f, X = 0.f, D = 0.f, Y = 0.f;
             if (comp) {
-                const float* qt = qring + dslot * kDiagElems + (kDiagRows - 1 - (s & (kDiagRows - 1))) * 96 + t;
+                const float* qt = qring + dslot * kDiagElems + (kDiagRows - 1 - (s & (kDiagRows - 1))) * kStepFloats + t;
                 e = zin + yprev;
                 if (i == n && c == m - 1) e = et;   // E[n, m] = Et (nw.py:125-127)
-                X = qt[0] * e;
-                D = qt[32] * e;
-                Y = qt[64] * e;
+                // q_m = (1 - q_x) - q_y is implied (>= 0: the forward stores q_y <= 1 - q_x)
+                const float qx = qt[0], qy = qt[kQY];
+                X = qx * e;
+                Y = qy * e;
+                D = ((1.f - qx) - qy) * e;
             }
             if (c >= 0 && c < m) etile[((c >> 5) & 1) * kTileElems + t * kTile + (c & 31)] = e;
             zout = X + dprev;

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) softdp_bwd2_kernel(BwdParams p) {
     pipe.reset();
 
     // tile a covers sweep steps [16a, 16a+16) = wavefront steps sigma in
-    // [m+15-16a, m+30-16a] of the strip, 6 KB contiguous; sweep step s reads row 15-(s&15)
+    // [m+15-16a, m+30-16a] of the strip, 4 KB contiguous; sweep step s reads row 15-(s&15)
     auto issue = [&](const Strip& st, int a, unsigned slot) {
         const int kb = st.K - 1 - st.k;
         const float* strip = p.Q + (long long)st.pair * p.ql.pair_stride + (long long)kb * p.ql.strip_stride;
@@ -153,9 +153,10 @@ __global__ void __launch_bounds__(256) softdp_bwd2_kernel(BwdParams p) {
                     float zin = __shfl_down_sync(kFull, zout, 1);
                     if (t == 31) zin = has_below ? br[-ss] : 0.f;
                     const float e = zin + yprev;
-                    const float X = qt[(15 - ss) * 96] * e;
-                    const float D = qt[(15 - ss) * 96 + 32] * e;
-                    const float Y = qt[(15 - ss) * 96 + 64] * e;
+                    const float qx = qt[(15 - ss) * kStepFloats], qy = qt[(15 - ss) * kStepFloats + kQY];
+                    const float X = qx * e;
+                    const float Y = qy * e;
+                    const float D = ((1.f - qx) - qy) * e;    // implied q_m (>= 0 by the forward's clamp)
                     st[ss * kB2StagePitch] = e;
                     zout = X + dprev;
                     dprev = D;
@@ -177,9 +178,10 @@ __global__ void __launch_bounds__(256) softdp_bwd2_kernel(BwdParams p) {
                     float e = zin + yprev;
                     if (seed_blk && i == n && c == m - 1) e = et;   // nw.py:125-127
                     e = comp ? e : 0.f;
-                    const float X = comp ? qt[(15 - ss) * 96] * e : 0.f;
-                    const float D = comp ? qt[(15 - ss) * 96 + 32] * e : 0.f;
-                    const float Y = comp ? qt[(15 - ss) * 96 + 64] * e : 0.f;
+                    const float qx = qt[(15 - ss) * kStepFloats], qy = qt[(15 - ss) * kStepFloats + kQY];
+                    const float X = comp ? qx * e : 0.f;
+                    const float Y = comp ? qy * e : 0.f;
+                    const float D = comp ? ((1.f - qx) - qy) * e : 0.f;
                     st[ss * kB2StagePitch] = e;
                     zout = X + dprev;
                     dprev = D;

@@ -9,8 +9,8 @@
 // lane that finishes its row starts the same row of the strip above on the next step.
 //   * Q: in the chained strip-major layout (strip_stride = M steps) the line of wavefront
 //     step sigma of strip kb+1 IS the line of step sigma + M of strip kb, so every lane of
-//     the warp -- whichever of two strips it is in -- reads the same 384-byte line, and the
-//     sweep walks a pair's Q storage sequentially from its end to its beginning: one 6 KB
+//     the warp -- whichever of two strips it is in -- reads the same 256-byte line, and the
+//     sweep walks a pair's Q storage sequentially from its end to its beginning: one 4 KB
 //     1-D bulk-TMA tile per 16 steps.  Only at a pair boundary two tiles are live (the
 //     first 31 lines of the old pair, the last lines of the new one).
 //   * E is staged step-major (pitch 33) and complete 32-column tiles are drained row-major
@@ -228,9 +228,10 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
                 float zin = __shfl_down_sync(kFull, zout, 1);
                 if (t == 31) zin = bv_[ss];
                 const float e = zin + yprev;
-                const float X = qt[(15 - ss) * 96] * e;
-                const float D = qt[(15 - ss) * 96 + 32] * e;
-                const float Y = qt[(15 - ss) * 96 + 64] * e;
+                const float qx = qt[(15 - ss) * kStepFloats], qy = qt[(15 - ss) * kStepFloats + kQY];
+                const float X = qx * e;
+                const float Y = qy * e;
+                const float D = ((1.f - qx) - qy) * e;        // implied q_m (>= 0 by the forward's clamp)
                 st[ss * kB2StagePitch] = e;
                 zout = X + dprev;
                 dprev = D;
@@ -267,10 +268,11 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
                     comp = ok && o != M - 1 && !(kb == 0 && t == 0);  // sw.py: i, j >= 2
                 }
                 e = comp ? e : 0.f;
-                const float* qt = ((has_tail && u > shat + ss) ? qtail : qmain) + t + (15 - ss) * 96;
-                const float X = comp ? qt[0] * e : 0.f;
-                const float D = comp ? qt[32] * e : 0.f;
-                const float Y = comp ? qt[64] * e : 0.f;
+                const float* qt = ((has_tail && u > shat + ss) ? qtail : qmain) + t + (15 - ss) * kStepFloats;
+                const float qx = qt[0], qy = qt[kQY];
+                const float X = comp ? qx * e : 0.f;
+                const float Y = comp ? qy * e : 0.f;
+                const float D = comp ? ((1.f - qx) - qy) * e : 0.f;
                 st[ss * kB2StagePitch] = e;
                 zout = X + dprev;
                 dprev = D;

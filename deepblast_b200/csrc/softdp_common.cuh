@@ -4,14 +4,20 @@
 //   theta, A, ZA : [B, N, M] fp32 row-major (reference layout, deepblast/nw.py:65-117)
 //   E, Ed, Ztheta: [B, N+2, M+2] fp32 row-major (reference layout, nw.py:347)
 //   Q, Qd        : the reference's [B, N+2, M+2, 3] (nw.py:105) stored STRIP-MAJOR in
-//                  the order the wavefront produces it.  Lattice cell (i, j), 1-based,
-//                  belongs to strip k = (i-1)/32, lane t = (i-1)%32 and is touched at
-//                  wavefront step sigma = (j-1) + t of that strip:
-//                    elem(b,i,j,s) = b*pair_stride + k*strip_stride + sigma*96 + s*32 + t
-//                    strip_stride = M*96, pair_stride = ceil(N/32)*strip_stride + 31*96
+//                  the order the wavefront produces it, TWO of the three states per cell:
+//                  the x and y components; the m component is implied (Q sums to 1 over
+//                  the states, Qd to 0: q_m = 1 - q_x - q_y, qd_m = -(qd_x + qd_y)), which
+//                  takes a third off the Q traffic of every sweep.  A cell whose Q is all
+//                  zero (first row / column of the sw.py lattice, sw.py:54-55) carries the
+//                  mark q_x = kQZeroMark (< 0, not a probability).
+//                  Lattice cell (i, j), 1-based, belongs to strip k = (i-1)/32, lane
+//                  t = (i-1)%32 and is touched at wavefront step sigma = (j-1) + t of that
+//                  strip:  elem(b,i,j,c) = b*pair_stride + k*strip_stride + sigma*64 + c*32 + t
+//                    (c = 0: x, c = 1: y)
+//                    strip_stride = M*64, pair_stride = ceil(N/32)*strip_stride + 31*64
 //                  (chained-dense: the 31 ramp steps of consecutive strips interleave
 //                  lane-wise, no step of a pair's storage is padding).
-//                  One step of a strip is 384 contiguous bytes (3 states x 32 lanes) and
+//                  One step of a strip is 256 contiguous bytes (2 states x 32 lanes) and
 //                  consecutive steps are contiguous, so the forward streams Q out
 //                  sequentially and the backward streams it back in with 1-D bulk TMA.
 //                  Border cells (zeros, Q[N+1,M+1,:]=1) are implicit, never stored.
@@ -26,7 +32,9 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kTile = 32;            // rows per strip == lanes; row-major tile is 32 x 32
 constexpr int kTileElems = kTile * kTile;
 constexpr int kRowRing = 3;          // theta/A (row-major, skewed read): 2 live tiles + 1 in flight
-constexpr int kStepFloats = 96;      // Q floats per wavefront step of a strip: 3 states x 32 lanes
+constexpr int kStepFloats = 64;      // Q floats per wavefront step of a strip: 2 stored states x 32 lanes
+constexpr int kQY = 32;              // offset of the y component inside a step (x at 0)
+constexpr float kQZeroMark = -1.0f;  // q_x of a cell whose Q is identically zero (sw.py first row / column)
 constexpr int kDiagRows = 16;        // wavefront steps per Q tile
 constexpr int kDiagElems = kDiagRows * kStepFloats;
 constexpr int kDiagRing = 4;         // Q tiles: 1 live + 3 in flight
@@ -251,7 +259,7 @@ __device__ __forceinline__ int progress_wait(const unsigned long long* word, uns
 
 struct QLayout {
     long long pair_stride;    // floats per pair  = K * strip_stride
-    long long strip_stride;   // floats per strip = M * 96 (consecutive strips overlap by 31 ramp steps)
+    long long strip_stride;   // floats per strip = M * 64 (consecutive strips overlap by 31 ramp steps)
     int K;                    // strips per pair  = ceil(N / 32)
 };
 

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) softdp_fwd_kernel(const __grid_constant__
             }
             const bool in = row_ok && j >= 1 && j <= m;
             const bool comp = in && i >= p.i0 && j >= p.i0;
-            float qx = 0.f, qm = 0.f, qy = 0.f, nh = 0.f, nl = 0.f;
+            float qx = 0.f, qy = 0.f, nh = 0.f, nl = 0.f;
             if (comp) {
                 const int c = j - 1;
                 const int o = (int)lslot * kTileElems + t * kTile + (c & 31);
@@ -156,9 +156,8 @@ __global__ void __launch_bounds__(256) softdp_fwd_kernel(const __grid_constant__
                 const float ey = fast_ex2((dy - mx) * kLog2e);
                 const float S = (ex + em) + ey;
                 const float r = fast_rcp(S);
-                qx = ex * r;
-                qm = em * r;
-                qy = ey * r;
+                qx = fminf(ex * r, 1.f);
+                qy = fminf(ey * r, 1.f - qx);        // keeps the implied q_m = (1 - q_x) - q_y >= 0
                 // V[i,j] = theta + V[i-1,j-1] + logsumexp(dx, 0, dy)   (nw.py:59-60)
                 const float delta = th + fmaf(fast_lg2(S), kLn2, mx);
                 const float t1 = delta + dl;
@@ -166,9 +165,9 @@ __global__ void __launch_bounds__(256) softdp_fwd_kernel(const __grid_constant__
                 nl = t1 - (nh - dh);
             }
             if (in) {
-                qp[0] = qx;
-                qp[32] = qm;
-                qp[64] = qy;
+                // two stored states; a cell below the sw.py origin (Q == 0) carries the mark
+                qp[0] = comp ? qx : kQZeroMark;
+                qp[kQY] = comp ? qy : kQZeroMark;
             }
             if (t == 31 && feeds_down && in) {
                 bnd_w[j - 1] = make_float2(nh, nl);

@@ -2,7 +2,7 @@
 // sw.py:46-62; replaces deepblast/nw_cuda.py:46-79).
 //
 // Same wavefront as softdp_fwd.cuh (lane t owns row 32k+t+1, one column per step, Q
-// streamed out strip-major, 384 contiguous bytes per step) re-organised for instruction
+// streamed out strip-major, 256 contiguous bytes per step) re-organised for instruction
 // count, dependent-chain length and occupancy:
 //   * DIFFERENCE FORM.  V itself is never formed.  Each lane carries v = V[i,j]-V[i-1,j]
 //     and hands h = V[i,j]-V[i,j-1] to the lane below; with a = A[i-1,j-1]
@@ -63,7 +63,10 @@ __device__ __forceinline__ float fwd2_step(float th, float a, float hup, float& 
     const float ey = fast_ex2(dy - mx);
     const float S = (em + ex) + ey;
     const float r = fast_rcp(S);
-    float qx = ex * r, qm = em * r, qy = ey * r;
+    // q_m = em * r is implied, never stored: readers form (1 - q_x) - q_y, which the clamp
+    // keeps >= 0 exactly (ex * r, or q_x + q_y, can round to 1 + 1 ulp when q_m underflows)
+    float qx = fminf(ex * r, 1.f);
+    float qy = fminf(ey * r, 1.f - qx);
     // l = theta + logsumexp = V[i,j] - V[i-1,j-1]   (nw.py:59-60)
     const float l = fast_lg2(S) + fmaf(th, kLog2e, mx);
     float hn = l - v;
@@ -74,17 +77,15 @@ __device__ __forceinline__ float fwd2_step(float th, float a, float hup, float& 
         hn = comp ? hn : 0.f;
         vn = comp ? vn : 0.f;
         if (SWM) {
-            qx = comp ? qx : 0.f;
-            qm = comp ? qm : 0.f;
-            qy = comp ? qy : 0.f;
+            qx = comp ? qx : kQZeroMark;             // Q == 0 below the sw.py origin: the mark
+            qy = comp ? qy : kQZeroMark;
         }
     }
     if (DBG & 1) {
-        if (qx + qm + qy == 12345.f) qp[0] = qx;     // keeps the math alive, never true
+        if (qx + qy == 12345.f) qp[0] = qx;          // keeps the math alive, never true
     } else if (!EDGE || store) {
         qp[0] = qx;
-        qp[32] = qm;
-        qp[64] = qy;
+        qp[kQY] = qy;
     }
     v = vn;
     return hn;

@@ -20,7 +20,7 @@
 //     in the same segment run the predicate-free unrolled "steady" code; the 2 NCH blocks
 //     per segment in which lanes roll over run the same step with per-lane selects.
 //   * the strip-major Q of consecutive strips is itself chained (strip_stride = M steps),
-//     so with NCH = 1 a pair is one sequential 384-byte-per-step stream end to end.
+//     so with NCH = 1 a pair is one sequential 256-byte-per-step stream end to end.
 //   * theta/A: TMA 16x16 boxes per 16-row group exactly as in softdp_fwd2.cuh; group j
 //     (16 j rows behind the leading edge) needs linear tile e - j in event e, so the
 //     consumer's shared-memory addressing does not know about segments at all.

@@ -76,8 +76,8 @@ __device__ __forceinline__ void row_tile_load_generic(float* dst, const RowSrc& 
     }
 }
 
-// ---- strip-major Q tile: kDiagRows consecutive wavefront steps = 6 KB contiguous -----
-// Loads steps [sig_lo, sig_lo + 16) of a strip into dst[16][3][32]; steps below 0 (the
+// ---- strip-major Q tile: kDiagRows consecutive wavefront steps = 4 KB contiguous -----
+// Loads steps [sig_lo, sig_lo + 16) of a strip into dst[16][2][32]; steps below 0 (the
 // last tile of a right-to-left sweep) are skipped and their slots left untouched.
 // kTMA: lane 0 arms the mbarrier (for expect_copies equal copies) and issues one 1-D bulk copy.  Otherwise every lane
 // issues 16-byte cp.async and the CALLER arrives (cp_async_mbar_arrive_noinc).

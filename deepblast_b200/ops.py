@@ -5,7 +5,9 @@ One function per private pass of the reference (deepblast/nw.py:65-117, 138-175,
 and streams only.  Q / Qd travel between the passes in the engine's STRIP-MAJOR layout
  as a 5-D strided view Q5[b, k, t, j-1, s] (strip k, lane t, i.e.
 lattice row i = 32k + t + 1); `q_to_reference` / `q_from_reference` convert to and
-from the reference's dense padded [B, N+2, M+2, 3].
+from the reference's dense padded [B, N+2, M+2, 3].  Only the x and y states of a cell
+are stored; the m state is implied (Q sums to 1 over the states, Qd to 0), and q_x = -1
+marks a cell whose Q is identically zero (first row / column of the sw.py lattice).
 """
 import torch
 
@@ -48,24 +50,24 @@ def _lens(xlen, ylen, B, N, M, device):
 
 
 def q_empty(B, N, M, device):
-    """Allocate strip-major storage; returns the 5-D view [B, K, 32, M, 3]."""
+    """Allocate strip-major storage; returns the 5-D view [B, K, 32, M, 2] (states x, y)."""
     K, ss, ps, pad = _lib.q_layout(N, M)
     storage = torch.empty(max(B, 1) * ps + pad, dtype=torch.float32, device=device)
-    return storage.as_strided((B, K, 32, M, 3), (ps, ss, 97, 96, 32), 0)
+    return storage.as_strided((B, K, 32, M, 2), (ps, ss, 65, 64, 32), 0)
 
 
 def _is_engine_q(Q, N, M):
     K, ss, ps, pad = _lib.q_layout(N, M)
-    return (Q.dim() == 5 and tuple(Q.shape[1:]) == (K, 32, M, 3) and Q.dtype == torch.float32
-            and tuple(Q.stride()[1:]) == (ss, 97, 96, 32) and (Q.shape[0] <= 1 or Q.stride(0) == ps)
+    return (Q.dim() == 5 and tuple(Q.shape[1:]) == (K, 32, M, 2) and Q.dtype == torch.float32
+            and tuple(Q.stride()[1:]) == (ss, 65, 64, 32) and (Q.shape[0] <= 1 or Q.stride(0) == ps)
             and Q.storage_offset() == 0 and Q.is_cuda)
 
 
-def _as_engine_q(Q, N=None, M=None):
+def _as_engine_q(Q, N=None, M=None, kind="q"):
     """Accept the engine's 5-D view or a dense reference-layout [B,N+2,M+2,3] tensor.
     Returns (Q5, N, M)."""
     if Q.dim() == 4 and Q.shape[-1] == 3:
-        return q_from_reference(Q), Q.shape[1] - 2, Q.shape[2] - 2
+        return q_from_reference(Q, kind), Q.shape[1] - 2, Q.shape[2] - 2
     if Q.dim() != 5 or N is None:
         raise RuntimeError("Q must be deepblast_b200's strip-major view (pass N) or a dense "
                            "[B, N+2, M+2, 3] reference-layout tensor")
@@ -76,27 +78,46 @@ def _as_engine_q(Q, N=None, M=None):
     return Q, N, M
 
 
-def q_from_reference(Qref):
-    """Dense reference-layout Q [B,N+2,M+2,3] -> engine layout (5-D view)."""
+def q_from_reference(Qref, kind="q"):
+    """Dense reference-layout Q (kind 'q') or Qd (kind 'qd') [B,N+2,M+2,3] -> engine layout
+    (5-D view).  The m state is dropped: it must be 1 - x - y for Q (a softmax; all-zero
+    cells are kept as marks) and -(x + y) for Qd."""
     if not Qref.is_cuda:
         raise RuntimeError("Q must be a CUDA tensor")
     B, N2, M2, _ = Qref.shape
     N, M = N2 - 2, M2 - 2
     Q5 = q_empty(B, N, M, Qref.device)
     K = Q5.shape[1]
-    rows = torch.zeros((B, K * 32, M, 3), dtype=torch.float32, device=Qref.device)
-    rows[:, :N] = Qref[:, 1:N + 1, 1:M + 1].float()
-    Q5.copy_(rows.view(B, K, 32, M, 3))
+    rows = torch.zeros((B, K * 32, M, 2), dtype=torch.float32, device=Qref.device)
+    inner = Qref[:, 1:N + 1, 1:M + 1].float()
+    xy = inner[..., 0::2]                                    # states x (0) and y (2)
+    if kind == "q":
+        zero = (inner == 0).all(dim=-1, keepdim=True)        # sw.py first row / column
+        # the implied m state (1 - x) - y must not go negative by a rounding of x + y
+        xy = torch.stack([xy[..., 0], torch.minimum(xy[..., 1], 1.0 - xy[..., 0])], dim=-1)
+        xy = torch.where(zero, torch.full_like(xy, -1.0), xy)
+    rows[:, :N] = xy
+    Q5.copy_(rows.view(B, K, 32, M, 2))
     return Q5
 
 
-def q_to_reference(Q5, N):
-    """Engine layout -> dense reference-layout [B,N+2,M+2,3] with the implicit borders
-    made explicit: zeros, and Q[N+1, M+1, :] = 1 (nw.py:51)."""
+def q_to_reference(Q5, N, kind="q"):
+    """Engine layout -> dense reference-layout [B,N+2,M+2,3] with the implied m state and
+    the implicit borders made explicit: zeros, and Q[N+1, M+1, :] = 1 (nw.py:51) for
+    kind 'q'; kind 'qd' (the adjoint's Qd) has m = -(x + y) and an all-zero border."""
     B, K, _, M, _ = Q5.shape
     out = torch.zeros((B, N + 2, M + 2, 3), dtype=torch.float32, device=Q5.device)
-    out[:, 1:N + 1, 1:M + 1] = Q5.reshape(B, K * 32, M, 3)[:, :N]
-    out[:, N + 1, M + 1] = 1.0
+    xy = Q5.reshape(B, K * 32, M, 2)[:, :N]
+    x, y = xy[..., 0], xy[..., 1]
+    if kind == "q":
+        zero = x < 0
+        m = (1.0 - x) - y
+        inner = torch.stack([x, m, y], dim=-1)
+        inner = torch.where(zero.unsqueeze(-1), torch.zeros_like(inner), inner)
+        out[:, N + 1, M + 1] = 1.0
+    else:
+        inner = torch.stack([x, -(x + y), y], dim=-1)
+    out[:, 1:N + 1, 1:M + 1] = inner
     return out
 
 
@@ -158,7 +179,7 @@ def adjoint_backward_pass(E, Q, Qd, xlen=None, ylen=None, flags=0):
     B, N2, M2 = E.shape
     N, M = N2 - 2, M2 - 2
     Q, _, _ = _as_engine_q(Q, N)
-    Qd, _, _ = _as_engine_q(Qd, N)
+    Qd, _, _ = _as_engine_q(Qd, N, kind="qd")
     _check_in("E", E, (B, N2, M2))
     E = E.detach().contiguous()
     xlen, ylen = _lens(xlen, ylen, B, N, M, Q.device)

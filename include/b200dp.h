@@ -60,7 +60,11 @@ const char* b200dp_last_error(void);
 
 /* Strip-major Q/Qd geometry for an N x M lattice (all in floats): strips per pair,
  * floats per strip, floats per pair, and the tail padding the allocation needs.
- * As a strided view: Q5[b, k, t, j-1, s] with strides (pair_stride, strip_stride, 97, 96, 32). */
+ * Two of the three states of a cell are stored (x, y); the m state is implied: q_m = 1 - q_x - q_y
+ * for Q, qd_m = -(qd_x + qd_y) for Qd; q_x = -1 marks a cell whose Q is identically zero
+ * (first row / column of the sw.py lattice).
+ * As a strided view: Q5[b, k, t, j-1, c] (c = 0: x, 1: y) with strides
+ * (pair_stride, strip_stride, 65, 64, 32). */
 int b200dp_q_layout(int N, int M, int* K, long long* strip_stride, long long* pair_stride,
                     long long* pad);
 

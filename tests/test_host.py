@@ -30,15 +30,15 @@ def test_q_layout_is_a_valid_strided_view():
     from deepblast_b200 import _lib
     for N, M in [(1, 1), (5, 4), (31, 33), (32, 32), (256, 256), (300, 77), (1000, 2047)]:
         K, ss, ps, pad = _lib.q_layout(N, M)
-        assert K == (N + 31) // 32 and ss == M * 96 and ps == K * ss + 31 * 96 and pad >= 16 * 96
-        # the 5-D view [K, 32, M, 3] with strides (ss, 97, 96, 32) addresses distinct
-        # elements inside the pair's storage: cell (i, j, s) -> k*ss + ((j-1)+t)*96 + s*32 + t
+        assert K == (N + 31) // 32 and ss == M * 64 and ps == K * ss + 31 * 64 and pad >= 16 * 64
+        # the 5-D view [K, 32, M, 2] (stored states x, y) with strides (ss, 65, 64, 32) addresses
+        # distinct elements inside the pair's storage: cell (i, j, c) -> k*ss + ((j-1)+t)*64 + c*32 + t
         if K * 32 * M <= 40000:
-            k, t, j0, s = np.meshgrid(np.arange(K), np.arange(32), np.arange(M), np.arange(3), indexing="ij")
-            addr = k * ss + t * 97 + j0 * 96 + s * 32
+            k, t, j0, s = np.meshgrid(np.arange(K), np.arange(32), np.arange(M), np.arange(2), indexing="ij")
+            addr = k * ss + t * 65 + j0 * 64 + s * 32
             assert addr.min() >= 0 and addr.max() < ps
             assert len(np.unique(addr)) == addr.size
-            np.testing.assert_array_equal(addr, k * ss + (j0 + t) * 96 + s * 32 + t)
+            np.testing.assert_array_equal(addr, k * ss + (j0 + t) * 64 + s * 32 + t)
 
 
 def test_argument_errors_do_not_need_a_gpu():
