@@ -30,7 +30,8 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("B200DP_NVCC_EXTRA", "").split()      # e.g. -DB200DP_DEBUG_WAIT (diagnostic builds)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
         ["-o", LIB, os.path.join(CSRC, "softdp_api.cu")]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB

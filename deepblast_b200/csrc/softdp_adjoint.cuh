@@ -30,7 +30,7 @@ __host__ __device__ inline size_t adj_fwd_smem_bytes(int W, int M) {
     size_t b = (size_t)W * kAdjFwdWarpBytes;
     b += (size_t)W * (kRowRing + kDiagRing) * 8;
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)(W + 1) * 8;
+    b += (size_t)(2 * W + 1) * 8;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)(W + 1) * (size_t)M * 8;
     return b;
@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(AdjFwdParams p) {
     off += (size_t)W * (kRowRing + kDiagRing) * 8;
     off = (off + 15) & ~(size_t)15;
     unsigned long long* prog = reinterpret_cast<unsigned long long*>(smem_raw + off);
-    off += (size_t)NB * 8;
+    unsigned long long* fin = prog + NB;      // per-warp finished-strip counters (run-ahead gate)
+    off += (size_t)(NB + W) * 8;
     off = (off + 15) & ~(size_t)15;
     float2* bnd = reinterpret_cast<float2*>(smem_raw + off);
 
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(AdjFwdParams p) {
         for (int s = 0; s < kDiagRing; ++s) mbar_init(&qbars[s], kTMA ? 1 : 32);
     }
     if ((int)threadIdx.x < NB) prog[threadIdx.x] = ~0ull;
+    if ((int)threadIdx.x < W) fin[threadIdx.x] = 0ull;
     fence_mbar_init();
     __syncthreads();
 
@@ -90,6 +92,7 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(AdjFwdParams p) {
     };
 
     while (cur.valid) {
+        strip_gate(fin, cur.q, w, W);
         const int n = cur.n, m = cur.m, k = cur.k;
         const int T = (m + kTile - 1) / kTile;
         const int Tn = nxt.valid ? (nxt.m + kTile - 1) / kTile : 0;
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(256) softdp_adj_fwd_kernel(AdjFwdParams p) {
         }
         rpipe.next_strip(T);
         qpipe.next_strip(Ta);
+        strip_done(fin, cur.q, w, W);
         cur = nxt;
         if (cur.valid) strip_next(nxt, p.d, w, W);
     }
@@ -216,7 +220,7 @@ __host__ __device__ inline size_t adj_bwd_smem_bytes(int W, int M) {
     size_t b = (size_t)W * kAdjBwdWarpBytes;
     b += (size_t)W * (kRowRing + kDiagRing) * 8;
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)(W + 1) * 8;
+    b += (size_t)(2 * W + 1) * 8;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)(W + 1) * (size_t)M * 4;
     return b;
@@ -239,7 +243,8 @@ __global__ void __launch_bounds__(256) softdp_adj_bwd_kernel(AdjBwdParams p) {
     off += (size_t)W * (kRowRing + kDiagRing) * 8;
     off = (off + 15) & ~(size_t)15;
     unsigned long long* prog = reinterpret_cast<unsigned long long*>(smem_raw + off);
-    off += (size_t)NB * 8;
+    unsigned long long* fin = prog + NB;      // per-warp finished-strip counters (run-ahead gate)
+    off += (size_t)(NB + W) * 8;
     off = (off + 15) & ~(size_t)15;
     float* bnd = reinterpret_cast<float*>(smem_raw + off);
 
@@ -248,6 +253,7 @@ __global__ void __launch_bounds__(256) softdp_adj_bwd_kernel(AdjBwdParams p) {
         for (int s = 0; s < kDiagRing; ++s) mbar_init(&qbars[s], kTMA ? 1 : 32);
     }
     if ((int)threadIdx.x < NB) prog[threadIdx.x] = ~0ull;
+    if ((int)threadIdx.x < W) fin[threadIdx.x] = 0ull;
     fence_mbar_init();
     __syncthreads();
 
@@ -294,6 +300,7 @@ __global__ void __launch_bounds__(256) softdp_adj_bwd_kernel(AdjBwdParams p) {
     };
 
     while (cur.valid) {
+        strip_gate(fin, cur.q, w, W);
         const int n = cur.n, m = cur.m;
         const int kb = cur.K - 1 - cur.k;
         const int T = (m + kTile - 1) / kTile;
@@ -394,6 +401,7 @@ __global__ void __launch_bounds__(256) softdp_adj_bwd_kernel(AdjBwdParams p) {
         }
         rpipe.next_strip(T);
         qpipe.next_strip(Ta);
+        strip_done(fin, cur.q, w, W);
         cur = nxt;
         if (cur.valid) strip_next(nxt, p.d, w, W);
     }

@@ -33,7 +33,7 @@ __host__ __device__ inline size_t bwd_smem_bytes(int W, int M) {
     size_t b = (size_t)W * kBwdWarpBytes;
     b += (size_t)W * kDiagRing * 8;
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)(W + 1) * 8;
+    b += (size_t)(2 * W + 1) * 8;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)(W + 1) * (size_t)M * 4;          // boundary rows (Z)
     return b;
@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(256) softdp_bwd_kernel(BwdParams p) {
     off += (size_t)W * kDiagRing * 8;
     off = (off + 15) & ~(size_t)15;
     unsigned long long* prog = reinterpret_cast<unsigned long long*>(smem_raw + off);
-    off += (size_t)NB * 8;
+    unsigned long long* fin = prog + NB;      // per-warp finished-strip counters (run-ahead gate)
+    off += (size_t)(NB + W) * 8;
     off = (off + 15) & ~(size_t)15;
     float* bnd = reinterpret_cast<float*>(smem_raw + off);
 
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256) softdp_bwd_kernel(BwdParams p) {
         for (int s = 0; s < kDiagRing; ++s) mbar_init(&bars[s], kTMA ? 1 : 32);
     }
     if ((int)threadIdx.x < NB) prog[threadIdx.x] = ~0ull;
+    if ((int)threadIdx.x < W) fin[threadIdx.x] = 0ull;
     fence_mbar_init();
     __syncthreads();
 
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(256) softdp_bwd_kernel(BwdParams p) {
     };
 
     while (cur.valid) {
+        strip_gate(fin, cur.q, w, W);
         const int n = cur.n, m = cur.m;
         const int kb = cur.K - 1 - cur.k;           // row block, processed bottom-up
         const int Ta = (m + 31 + kDiagRows - 1) / kDiagRows;
@@ -179,6 +182,7 @@ __global__ void __launch_bounds__(256) softdp_bwd_kernel(BwdParams p) {
             Eb[(long long)(N + 1) * (M + 2) + M + 1] = et;   // caller pre-zeroed E
         }
         pipe.next_strip(Ta);
+        strip_done(fin, cur.q, w, W);
         cur = nxt;
         if (cur.valid) strip_next(nxt, p.d, w, W);
     }

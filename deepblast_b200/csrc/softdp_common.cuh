@@ -25,6 +25,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef B200DP_DEBUG_WAIT
+#include <cstdio>
+#endif
 
 namespace b200dp {
 
@@ -253,7 +256,42 @@ __device__ __forceinline__ int progress_wait(const unsigned long long* word, uns
         unsigned long long v = ld_acquire_u64(word);
         if ((unsigned)(v >> 32) == q && (int)(unsigned)v >= need) return (int)(unsigned)v;
         __nanosleep(32);
+#ifdef B200DP_DEBUG_WAIT
+        if (++spins > (1u << 18)) {
+            if ((threadIdx.x & 31) == 0)
+                printf("progress_wait stuck: cta %d warp %d wants q %u need %d, word q %u count %d\n", (int)blockIdx.x,
+                       (int)(threadIdx.x >> 5), q, need, (unsigned)(v >> 32), (int)(unsigned)v);
+            return need;
+        }
+#else
         if (++spins > kSpinLimit) __trap();
+#endif
+    }
+}
+
+// ---- run-ahead gate ------------------------------------------------------------------
+// Boundary slot q % (W+1) is reused by strip q + (W+1).  Inside one pair the hand-off chain
+// itself keeps a writer behind the previous reader of its slot, but the first strip of a
+// pair waits for nobody, so across pair boundaries (ragged batches, many short pairs per
+// CTA) a warp could run several strips ahead of its left neighbour and overwrite a row --
+// and its progress word -- that a slow warp is still reading.  Gate: strip q starts only
+// after strip q - (W+1), the previous strip of warp w-1, has finished; by induction every
+// earlier user of the slot has finished too.  fin[w] = 1 + the last strip warp w finished.
+__device__ __forceinline__ void strip_gate(const unsigned long long* fin, unsigned q, int w, int W) {
+    if (W > 1 && q >= (unsigned)(W + 1)) {
+        const unsigned long long* f = fin + ((w + W - 1) % W);
+        const unsigned long long want = (unsigned long long)q - (unsigned)W;      // 1 + (q - (W+1))
+        unsigned spins = 0;
+        while (ld_acquire_u64(f) < want) {
+            __nanosleep(32);
+            if (++spins > kSpinLimit) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void strip_done(unsigned long long* fin, unsigned q, int w, int W) {
+    if (W > 1) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) st_release_u64(fin + w, (unsigned long long)q + 1ull);
     }
 }
 

@@ -33,7 +33,7 @@ __host__ __device__ inline size_t fwd_smem_bytes(int W, int M) {
     size_t b = (size_t)W * kFwdWarpBytes;
     b += (size_t)W * kRowRing * 8;                 // mbarriers
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)(W + 1) * 8;                      // progress words
+    b += (size_t)(2 * W + 1) * 8;                      // progress words
     b = (b + 15) & ~(size_t)15;
     b += (size_t)(W + 1) * (size_t)M * 8;          // boundary rows (hi, lo)
     return b;
@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(256) softdp_fwd_kernel(const __grid_constant__
     off += (size_t)W * kRowRing * 8;
     off = (off + 15) & ~(size_t)15;
     unsigned long long* prog = reinterpret_cast<unsigned long long*>(smem_raw + off);
-    off += (size_t)NB * 8;
+    unsigned long long* fin = prog + NB;      // per-warp finished-strip counters (run-ahead gate)
+    off += (size_t)(NB + W) * 8;
     off = (off + 15) & ~(size_t)15;
     float2* bnd = reinterpret_cast<float2*>(smem_raw + off);
 
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256) softdp_fwd_kernel(const __grid_constant__
         for (int s = 0; s < kRowRing; ++s) mbar_init(&bars[s], kTMA ? 1 : 32);
     }
     if ((int)threadIdx.x < NB) prog[threadIdx.x] = ~0ull;
+    if ((int)threadIdx.x < W) fin[threadIdx.x] = 0ull;
     fence_mbar_init();
     __syncthreads();
     if (kTMA && threadIdx.x == 0) {
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(256) softdp_fwd_kernel(const __grid_constant__
     };
 
     while (cur.valid) {
+        strip_gate(fin, cur.q, w, W);
         const int n = cur.n, m = cur.m, k = cur.k;
         const int T = (m + kTile - 1) / kTile;
         const int Tn = nxt.valid ? (nxt.m + kTile - 1) / kTile : 0;
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(256) softdp_fwd_kernel(const __grid_constant__
             qp += kStepFloats;
         }
         pipe.next_strip(T);
+        strip_done(fin, cur.q, w, W);
         cur = nxt;
         if (cur.valid) strip_next(nxt, p.d, w, W);
     }

@@ -35,7 +35,7 @@ __host__ __device__ inline size_t fwd2_smem_bytes(int W, int M) {
     size_t b = (size_t)W * RING * kF2SlotBytes;
     b += (size_t)W * RING * 8;
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)(W + 1) * 8;
+    b += (size_t)(2 * W + 1) * 8;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)(W + 1) * (size_t)M * 4;
     b += 256;                                      // 16 zeros (row above a pair) + slack for ramp reads
@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
     off += (size_t)W * kF2Ring * 8;
     off = (off + 15) & ~(size_t)15;
     unsigned long long* prog = reinterpret_cast<unsigned long long*>(smem_raw + off);
-    off += (size_t)NB * 8;
+    unsigned long long* fin = prog + NB;      // per-warp finished-strip counters (run-ahead gate)
+    off += (size_t)(NB + W) * 8;
     off = (off + 15) & ~(size_t)15;
     float* bnd = reinterpret_cast<float*>(smem_raw + off);
 
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
         for (int s = 0; s < kF2Ring; ++s) mbar_init(&bars[s], 1);
     }
     if ((int)threadIdx.x < NB) prog[threadIdx.x] = ~0ull;
+    if ((int)threadIdx.x < W) fin[threadIdx.x] = 0ull;
     fence_mbar_init();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
     };
 
     while (cur.valid) {
+        strip_gate(fin, cur.q, w, W);
         const int n = cur.n, m = cur.m, k = cur.k;
         const int T16 = (m + kG - 1) / kG;
         const int NE = T16 + 1;                       // events of this strip
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(256) softdp_fwd2_kernel(const __grid_constant_
             }
         }
         pipe.next_strip(NE);
+        strip_done(fin, cur.q, w, W);
         cur = nxt;
         if (cur.valid) strip_next(nxt, p.d, w, W);
     }

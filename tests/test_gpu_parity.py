@@ -353,3 +353,40 @@ def test_end_to_end_traceback_agreement(ops):
     _, _, E_o = O.decode(theta.numpy(), A.numpy(), "nw")
     for b in range(B):
         assert got[b] == O.traceback(E_o[b, 1:-1, 1:-1], "cuda")
+
+
+@pytest.mark.parametrize("kern", [0, V1])
+def test_ragged_many_pairs_per_cta_handoff(ops, kern):
+    """Regression: many short ragged pairs per persistent CTA with 8 warps per pair.  The first
+    strip of a pair waits for nobody, so without the run-ahead gate (strip_gate,
+    softdp_common.cuh) a warp ran several strips ahead of its neighbour and overwrote a
+    boundary row / progress word still in use: the sweep dead-locked (BASELINE configs[4]
+    at 1024 pairs per GPU).  W = 8 must finish and agree with W = 1 and with the oracle."""
+    B, kmax = 1024, 6
+    rng = np.random.default_rng(0)
+    k = np.arange(1, kmax + 1)
+    pk = (1.0 / k) / (1.0 / k).sum()
+    xl = 64 * rng.choice(k, size=B, p=pk)
+    yl = 64 * rng.choice(k, size=B, p=pk)
+    N = M = 64 * kmax
+    g = torch.Generator(device=dev()).manual_seed(3)
+    th = torch.rand(B, N, M, generator=g, device=dev())
+    a = -torch.rand(B, N, M, generator=g, device=dev())
+    xlen = torch.tensor(xl, dtype=torch.int32, device=dev())
+    ylen = torch.tensor(yl, dtype=torch.int32, device=dev())
+    Et = torch.ones(B, device=dev())
+    res = {}
+    for W in (8, 1):
+        fl = (W << 4) | kern
+        Vt, Q = ops.forward_pass(th, a, "nw", xlen, ylen, flags=fl)
+        E = ops.backward_pass(Et, Q, "nw", xlen, ylen, flags=fl, N=N)
+        torch.cuda.synchronize()
+        res[W] = (Vt, E)
+    assert torch.allclose(res[8][0], res[1][0], rtol=1e-6)
+    assert torch.allclose(res[8][1], res[1][1], rtol=0, atol=2e-6)
+    for b in (0, 17, 500, 1023):
+        n, m = int(xl[b]), int(yl[b])
+        Vt_o, Q_o = O.forward_pass(th[b:b + 1, :n, :m].cpu().numpy(), a[b:b + 1, :n, :m].cpu().numpy(), "nw")
+        E_o = O.backward_pass(np.ones(1, np.float32), Q_o, "nw")
+        np.testing.assert_allclose(res[8][0][b].item(), Vt_o[0], rtol=1e-6)
+        np.testing.assert_allclose(res[8][1][b, 1:n + 1, 1:m + 1].cpu().numpy(), E_o[0, 1:-1, 1:-1], rtol=0, atol=ATOL_QE * 2)
