@@ -1,0 +1,17 @@
+#!/bin/bash
+# 2-rank torchrun runs of bench.py (needs gpurun --gpus 2): c2, c4, c5 and the reference arm.
+mkdir -p gpurun_out
+port=29540
+for w in c2 c4 c5; do
+  port=$((port+1))
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $port bench.py --gpus 2 --workload $w --steps 10 --warmup 3 > gpurun_out/bench_2gpu_$w.log 2>&1; echo "$w rc=$?"
+  tail -1 gpurun_out/bench_2gpu_$w.log | python -c "
+import json,sys
+try:
+    d=json.loads(sys.stdin.read()); r=d['roofline']
+    print('n_gpus %d value %.1f G  ms/step %.3f  fwd %.3f bwd %.3f  e2e %.2f G  %s' % (d['n_gpus'], d['value']/1e9, d['ms_per_step'], r['fwd']['ms'], r['bwd']['ms'], d['e2e']['value']/1e9, d['config'].get('packing','')))
+except Exception as e: print('parse fail', e)
+"
+done
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29550 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 --cpu-seconds 2 > gpurun_out/bench_2gpu_ref.log 2>&1; echo "ref rc=$?"
+tail -1 gpurun_out/bench_2gpu_ref.log | cut -c1-200
