@@ -208,7 +208,8 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
         const bool fullL = (kbL + 1) * kTile <= N;
         const float* br = (Lvalid && kL > 0) ? bnd + posS : zero_row;
         float* st = stage + srow * kB2StagePitch + t;
-        const bool sw_special = SWM && (kbL == 0 || posS == M - 16);
+        const bool sw_special = SWM && posS == M - 16;        // column 1 (sw.py: j >= 2) is swept in this block
+        const bool sw_dead = SWM && kbL == 0 && t == 0;       // row 1 (sw.py: i >= 2): E = 0, nothing pushed
 
         if (plain && Lvalid && fullL && !sw_special) {
             // ---- steady block ---------------------------------------------------------------
@@ -223,15 +224,26 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
                 bv_[4 * q4 + 2] = b4.z;
                 bv_[4 * q4 + 3] = b4.w;
             }
+            // the block's own Q (32 LDS) and the implied q_m up front: the staging / boundary
+            // stores inside the loop may alias the Q ring as far as the compiler knows, so loads
+            // left in the loop would be serialised behind them, one shared-memory latency per step
+            float qx_[16], qy_[16], qm_[16];
+#pragma unroll
+            for (int ss = 0; ss < 16; ++ss) {
+                qx_[ss] = qt[(15 - ss) * kStepFloats];
+                qy_[ss] = qt[(15 - ss) * kStepFloats + kQY];
+            }
+#pragma unroll
+            for (int ss = 0; ss < 16; ++ss) qm_[ss] = (1.f - qx_[ss]) - qy_[ss];   // >= 0 by the forward's clamp
 #pragma unroll
             for (int ss = 0; ss < 16; ++ss) {
                 float zin = __shfl_down_sync(kFull, zout, 1);
                 if (t == 31) zin = bv_[ss];
-                const float e = zin + yprev;
-                const float qx = qt[(15 - ss) * kStepFloats], qy = qt[(15 - ss) * kStepFloats + kQY];
-                const float X = qx * e;
-                const float Y = qy * e;
-                const float D = ((1.f - qx) - qy) * e;        // implied q_m (>= 0 by the forward's clamp)
+                float e = zin + yprev;
+                if (SWM) e = sw_dead ? 0.f : e;               // the marks are finite: 0 * mark = 0
+                const float X = qx_[ss] * e;
+                const float Y = qy_[ss] * e;
+                const float D = qm_[ss] * e;
                 st[ss * kB2StagePitch] = e;
                 zout = X + dprev;
                 dprev = D;

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
 #pragma unroll
         for (int c = 0; c < NCH; ++c) part[c] = 0.f;
 
-        if (plain && Lvalid && fullL && !(SWM && passL == 0)) {
+        if (plain && Lvalid && fullL) {
             // ---- steady block: one segment, every row inside the lattice ------------------
             const int pairL = pair_of(idxL);
             float* qb = p.Q + (long long)pairL * PS + (long long)(passL * NCH) * SS + (long long)posL * kStepFloats + t;
@@ -214,7 +214,10 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
                     const float hup = (t == 0) ? (c == 0 ? bv_[ss] : r[c > 0 ? c - 1 : 0]) : r[c];
                     // chain c: strip passL*NCH + c, wavefront step posL + ss - 32 c of that strip
                     float* qp = qb + (long long)c * (SS - 32 * kStepFloats) + ss * kStepFloats;
-                    h[c] = fwd2_step<false, false, DBG>(th_[c][ss], a_[c][ss], hup, v[c], qp, true, true);
+                    // sw.py: row 1 (lane 0 of the pair's first strip) is below the origin -- V = 0, Q = 0
+                    // (column 1 is always met in a roll-over block, i.e. in the general path)
+                    const bool live = !(SWM && c == 0 && t == 0 && passL == 0);
+                    h[c] = fwd2_step<false, SWM, DBG>(th_[c][ss], a_[c][ss], hup, v[c], qp, true, live);
                     part[c] += h[c];
                 }
                 if (t == 31) bw[ss] = h[NCH - 1];

@@ -181,8 +181,10 @@ def test_decode_host_matches_device_path_and_oracle(mode, B, N, M, chunk):
     aln = dec.decode(theta, A)
     Vt = dec(theta, A)
     torch.cuda.synchronize()
-    assert torch.equal(g_h, aln.detach().cpu())
-    assert torch.equal(Vt_h, Vt.detach().cpu())
+    # chunks go through the hand-off kernels, the full batch may go through the chained ones:
+    # same arithmetic, but the compiler may contract different multiply-adds
+    assert torch.allclose(g_h, aln.detach().cpu(), rtol=0, atol=1e-6)
+    assert torch.allclose(Vt_h, Vt.detach().cpu(), rtol=1e-6)
     nb = min(B, 6)
     Vt_o, Q_o, E_o = O.decode(theta_h[:nb].numpy(), A_h[:nb].numpy(), mode)
     np.testing.assert_allclose(g_h[:nb].numpy(), E_o[:, 1:-1, 1:-1], atol=1e-4, rtol=1e-4)
