@@ -63,6 +63,26 @@ def zipf_lengths(B, rng):
     return 64 * rng.choice(k, size=B, p=pk), 64 * rng.choice(k, size=B, p=pk)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and so the pinned host buffers it first-touches) to the CPU cores
+    NVML reports as local to GPU `index`: host<->device copies then stay on the GPU's own
+    socket instead of crossing the inter-socket link.  Returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} GPU-local cores"
+        return "no GPU-local cores reported"
+    except Exception as e:      # no NVML / not permitted: run unbound
+        return f"unbound ({type(e).__name__})"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -197,6 +217,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the process to the GPU-local CPU cores")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -214,6 +235,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa_node(local) if not args.no_bind else "unbound (--no-bind)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if world != args.gpus and rank == 0:
@@ -356,7 +378,7 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": total_cells * nst / (float(te.item()) * 1e-3), "unit": "cell-updates/s",
                "h2d_bytes_per_step": int(2 * Bg * N * M * 4), "d2h_bytes_per_step": d2h,
-               "ms_per_step": float(te.item()) / nst, "steps": nst, "note": note}
+               "ms_per_step": float(te.item()) / nst, "steps": nst, "host_affinity": affinity, "note": note}
 
     if rank == 0:
         peak, peak_src = peaks()
