@@ -19,6 +19,7 @@
 #include "softdp_fwd.cuh"
 #include "softdp_fwd2.cuh"
 #include "softdp_fwd3.cuh"
+#include "softdp_loss.cuh"
 #include "softdp_traceback.cuh"
 
 using namespace b200dp;
@@ -147,7 +148,8 @@ int pick_geometry(const char* fn, int B, int N, int M, int flags, SmemFn smem_of
         // ragged batches: the host does not know the lengths, but a CTA's strips form one
         // sequence across pairs, so short pairs do not idle the warps of a wide CTA while
         // long pairs need the width: keep the widest CTA that fits
-        if (!forceW && varlen && W < 8 && W < K && smem_of(2 * W, M) <= (size_t)di.smem_optin) continue;
+        // (skip W only when 2 W is itself admissible: 2 W <= K and it fits)
+        if (!forceW && varlen && W < 8 && 2 * W <= K && smem_of(2 * W, M) <= (size_t)di.smem_optin) continue;
         size_t smem = smem_of(W, M);
         if (smem > (size_t)di.smem_optin) continue;
         int per_sm = (int)((size_t)di.smem_per_sm / (smem + 1024));   // 1 KB reserved per CTA
@@ -630,6 +632,38 @@ int b200dp_traceback(const float* grad, long long sb, long long si, long long sj
     softdp_traceback_kernel<<<(B + threads - 1) / threads, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "b200dp_traceback launch");
+    return 0;
+}
+
+int b200dp_mxent_fwd(const float* Ytrue, const float* Ypred, long long pb, long long pi, const float* G,
+                     const int32_t* xlen, const int32_t* ylen, int B, int N, int M, float* pair_loss,
+                     float* pair_count, void* stream) {
+    if (int rc = check_common("b200dp_mxent_fwd", B, N, M)) return rc;
+    if (B == 0) return 0;
+    if (!Ytrue || !Ypred || !pair_loss || !pair_count) return fail(-1, "b200dp_mxent_fwd: null pointer");
+    LossParams p{};
+    p.Ytrue = Ytrue; p.Ypred = Ypred; p.G = G; p.xlen = xlen; p.ylen = ylen;
+    p.pb = pb; p.pi = pi; p.B = B; p.N = N; p.M = M;
+    p.pair_loss = pair_loss; p.pair_count = pair_count;
+    softdp_mxent_fwd_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "b200dp_mxent_fwd launch");
+    return 0;
+}
+
+int b200dp_mxent_bwd(const float* Ytrue, const float* Ypred, long long pb, long long pi, const float* G,
+                     const int32_t* xlen, const int32_t* ylen, int B, int N, int M, const float* pair_count,
+                     const float* gout, float* grad, void* stream) {
+    if (int rc = check_common("b200dp_mxent_bwd", B, N, M)) return rc;
+    if (B == 0) return 0;
+    if (!Ytrue || !Ypred || !pair_count || !gout || !grad) return fail(-1, "b200dp_mxent_bwd: null pointer");
+    LossParams p{};
+    p.Ytrue = Ytrue; p.Ypred = Ypred; p.G = G; p.xlen = xlen; p.ylen = ylen;
+    p.pb = pb; p.pi = pi; p.B = B; p.N = N; p.M = M;
+    p.pair_count = const_cast<float*>(pair_count); p.gout = gout; p.grad = grad;
+    softdp_mxent_bwd_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "b200dp_mxent_bwd launch");
     return 0;
 }
 

@@ -102,6 +102,20 @@ int b200dp_traceback(const float* grad, long long sb, long long si, long long sj
                      const int32_t* xlen, const int32_t* ylen, int B, int N, int M,
                      int variant, int32_t* out, int cap, int32_t* len, void* stream);
 
+/* replaces the per-pair Python loop of MatrixCrossEntropy.__call__, deepblast/losses.py:9-48
+ * (trainer.py:154-171), the step right after decode: Ytrue, G [B, N, M] contiguous (G NULL =
+ * all counted), Ypred [B, N, M] with element strides (pb, pi, 1) -- e.g. the padded E in
+ * place -- and optional per-pair lengths -> pair_loss[b] = l_b / B (loss = sum_b) and
+ * pair_count[b]; the backward writes dloss/dYpred [B, N, M] (zeros outside the mask)
+ * scaled by the scalar gout[0]. */
+int b200dp_mxent_fwd(const float* Ytrue, const float* Ypred, long long pb, long long pi,
+                     const float* G, const int32_t* xlen, const int32_t* ylen, int B, int N,
+                     int M, float* pair_loss, float* pair_count, void* stream);
+int b200dp_mxent_bwd(const float* Ytrue, const float* Ypred, long long pb, long long pi,
+                     const float* G, const int32_t* xlen, const int32_t* ylen, int B, int N,
+                     int M, const float* pair_count, const float* gout, float* grad,
+                     void* stream);
+
 /* Host-buffer form of NeedlemanWunschDecoder.decode (deepblast/nw_cuda.py:319-325: forward,
  * then autograd.grad of sum(Vt), i.e. _forward_pass_kernel + _backward_pass_kernel) for a
  * caller whose theta / A live in HOST memory (pinned for full PCIe speed):

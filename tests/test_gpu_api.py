@@ -202,3 +202,78 @@ def test_decode_host_rejects_cuda_and_bad_dtype():
         ops.decode_host(t.to(dev()), t, "nw")
     with pytest.raises(TypeError):
         ops.decode_host(t.double(), t.double(), "nw")
+
+
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+@pytest.mark.parametrize("variant", ["cuda", "cpu"])
+def test_traceback_pairs_matches_per_pair_reference_loop(mode, variant):
+    """deepblast_b200.align.traceback_pairs == the loop of NeuralAligner.traceback
+    (alignment.py:160-171): per pair, decode on the [xlen, ylen] slices, then the walk."""
+    from deepblast_b200 import align
+    from oracle import softdp as O
+    B, N, M = 9, 72, 60
+    g = torch.Generator().manual_seed(11)
+    match = torch.rand(B, N, M, generator=g)
+    gap = -torch.rand(B, N, M, generator=g)
+    xlen = [72, 5, 33, 64, 17, 70, 32, 48, 9]
+    ylen = [60, 60, 31, 7, 17, 59, 32, 50, 40]
+    dec = decoders()[mode]('softmax')
+    strings, decoded, alns = align.align_batch(dec, match.to(dev()), gap.to(dev()), xlen, ylen, variant)
+    for b in range(B):
+        n, m = xlen[b], ylen[b]
+        Vt_o, Q_o, E_o = O.decode(match[b:b + 1, :n, :m].numpy(), gap[b:b + 1, :n, :m].numpy(), mode)
+        assert tuple(alns[b].shape) == (1, n, m)
+        np.testing.assert_allclose(alns[b][0].detach().cpu().numpy(), E_o[0, 1:-1, 1:-1], rtol=0, atol=2e-5)
+        # the walk is compared on the SAME matrix (ours): near-ties must not make the test flaky
+        want = O.traceback(alns[b][0].detach().cpu().numpy(), variant)
+        assert decoded[b] == want
+        assert strings[b] == ''.join({0: '1', 1: ':', 2: '2'}[s] for _, _, s in want)
+
+
+@pytest.fixture(scope="module")
+def loss_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_golden.npz"))
+
+
+@pytest.mark.parametrize("name", ["small", "ragged", "saturated"])
+def test_matrix_cross_entropy_matches_reference_golden(loss_golden, name):
+    """Fused MatrixCrossEntropy vs vectors generated by the reference's own
+    deepblast.losses.MatrixCrossEntropy (tests/golden/make_loss_golden.py)."""
+    from deepblast_b200.losses import MatrixCrossEntropy
+    g = lambda k: loss_golden[f"{name}/{k}"]
+    Ypred = torch.from_numpy(g("Ypred")).to(dev()).requires_grad_()
+    loss = MatrixCrossEntropy()(torch.from_numpy(g("Ytrue")).to(dev()), Ypred, g("xlen").tolist(),
+                                g("ylen").tolist(), torch.from_numpy(g("G")).to(dev()))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), float(g("loss")), rtol=2e-6)
+    np.testing.assert_allclose(Ypred.grad.cpu().numpy(), g("grad"), rtol=1e-5, atol=1e-7)
+
+
+def test_matrix_cross_entropy_on_decode_output():
+    """The loss reads predA = decode(theta, A) in place (a strided view of the padded E) and
+    its gradient flows back through the adjoint sweeps, as in trainer.py:154-171,192-199."""
+    from deepblast_b200.losses import MatrixCrossEntropy
+    B, N, M = 5, 40, 48
+    g = torch.Generator().manual_seed(3)
+    theta = torch.rand(B, N, M, generator=g).to(dev()).requires_grad_()
+    A = (-torch.rand(B, N, M, generator=g)).to(dev()).requires_grad_()
+    Ytrue = (torch.rand(B, N, M, generator=g) < 0.05).float().to(dev())
+    G = torch.ones(B, N, M, device=dev())
+    xlen, ylen = [40, 33, 40, 8, 25], [48, 48, 17, 30, 41]
+    dec = decoders()["nw"]('softmax')
+    predA = dec.decode(theta, A)
+    assert not predA.is_contiguous()
+    loss = MatrixCrossEntropy()(Ytrue, predA, xlen, ylen, G)
+    # the reference's formula, stated with torch ops
+    ref = 0
+    P = torch.clamp(predA, min=3e-8, max=1 - 3e-8)
+    for b in range(B):
+        sl = (b, slice(0, xlen[b]), slice(0, ylen[b]))
+        ref = ref - torch.mean(Ytrue[sl] * torch.log(P[sl]) + (1 - Ytrue[sl]) * torch.log(1 - P[sl]))
+    ref = ref / B
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-5)
+    g1, = torch.autograd.grad(loss, theta, retain_graph=True)
+    g2, = torch.autograd.grad(ref, theta)
+    scale = float(g2.abs().max())
+    np.testing.assert_allclose(g1.cpu().numpy(), g2.cpu().numpy(), rtol=0, atol=2e-4 * scale)
