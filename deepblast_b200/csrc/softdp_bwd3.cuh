@@ -19,6 +19,8 @@
 //     boundary row of M floats per warp.
 // Requirements (checked by the host): no per-pair lengths, M % 32 == 0, M >= 64.
 #pragma once
+#include <type_traits>
+
 #include "softdp_bwd2.cuh"
 
 namespace b200dp {
@@ -211,45 +213,70 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
         const bool sw_special = SWM && posS == M - 16;        // column 1 (sw.py: j >= 2) is swept in this block
         const bool sw_dead = SWM && kbL == 0 && t == 0;       // row 1 (sw.py: i >= 2): E = 0, nothing pushed
 
-        if (plain && Lvalid && fullL && !sw_special) {
-            // ---- steady block ---------------------------------------------------------------
-            const float* qt = qmain + t;
-            float* bw = bnd + (posS - 31);
-            float bv_[16];
+        // roll-over inside one pair, both strips complete: the steady step plus the row-start
+        // resets (no tail tile, no partial rows, no seed; sw.py's column 1 stays on the general path)
+        const bool simple_roll = !SWM && !plain && Lvalid && kL > 0 && (kbL + 2) * kTile <= N;
+        if ((plain && Lvalid && fullL && !sw_special) || simple_roll) {
+            // ---- steady block (ROLL = false) / simple roll-over block (ROLL = true) ----------
+            auto body = [&](auto roll_tag) {
+                constexpr bool ROLL = decltype(roll_tag)::value;
+                const float* qt = qmain + t;
+                const int roll = u - posS;                    // ROLL: step at which the lane enters L
+                float* bw = bnd + (posS - 31);
+                float bv_[16];
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                const float4 b4 = reinterpret_cast<const float4*>(br)[q4];
-                bv_[4 * q4] = b4.x;
-                bv_[4 * q4 + 1] = b4.y;
-                bv_[4 * q4 + 2] = b4.z;
-                bv_[4 * q4 + 3] = b4.w;
-            }
-            // the block's own Q (32 LDS) and the implied q_m up front: the staging / boundary
-            // stores inside the loop may alias the Q ring as far as the compiler knows, so loads
-            // left in the loop would be serialised behind them, one shared-memory latency per step
-            float qx_[16], qy_[16], qm_[16];
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 b4 = reinterpret_cast<const float4*>(br)[q4];
+                    bv_[4 * q4] = b4.x;
+                    bv_[4 * q4 + 1] = b4.y;
+                    bv_[4 * q4 + 2] = b4.z;
+                    bv_[4 * q4 + 3] = b4.w;
+                }
+                // the block's own Q (32 LDS) and the implied q_m up front: the staging / boundary
+                // stores inside the loop may alias the Q ring as far as the compiler knows, so loads
+                // left in the loop would be serialised behind them, one shared-memory latency per step
+                float qx_[16], qy_[16], qm_[16];
 #pragma unroll
-            for (int ss = 0; ss < 16; ++ss) {
-                qx_[ss] = qt[(15 - ss) * kStepFloats];
-                qy_[ss] = qt[(15 - ss) * kStepFloats + kQY];
-            }
+                for (int ss = 0; ss < 16; ++ss) {
+                    qx_[ss] = qt[(15 - ss) * kStepFloats];
+                    qy_[ss] = qt[(15 - ss) * kStepFloats + kQY];
+                }
 #pragma unroll
-            for (int ss = 0; ss < 16; ++ss) qm_[ss] = (1.f - qx_[ss]) - qy_[ss];   // >= 0 by the forward's clamp
+                for (int ss = 0; ss < 16; ++ss) qm_[ss] = (1.f - qx_[ss]) - qy_[ss];   // >= 0 by the forward's clamp
 #pragma unroll
-            for (int ss = 0; ss < 16; ++ss) {
-                float zin = __shfl_down_sync(kFull, zout, 1);
-                if (t == 31) zin = bv_[ss];
-                float e = zin + yprev;
-                if (SWM) e = sw_dead ? 0.f : e;               // the marks are finite: 0 * mark = 0
-                const float X = qx_[ss] * e;
-                const float Y = qy_[ss] * e;
-                const float D = qm_[ss] * e;
-                st[ss * kB2StagePitch] = e;
-                zout = X + dprev;
-                dprev = D;
-                yprev = Y;
-                if (t == 0) bw[ss] = zout;
-            }
+                for (int ss = 0; ss < 16; ++ss) {
+                    float zin = __shfl_down_sync(kFull, zout, 1);
+                    if (t == 31) zin = bv_[ss];
+                    if (ROLL) {
+                        // a lane that starts a new row has nothing to its right
+                        const bool at = ss == roll;
+                        yprev = at ? 0.f : yprev;
+                        dprev = at ? 0.f : dprev;
+                    }
+                    float e = zin + yprev;
+                    if (SWM) e = sw_dead ? 0.f : e;           // the marks are finite: 0 * mark = 0
+                    const float X = qx_[ss] * e;
+                    const float Y = qy_[ss] * e;
+                    const float D = qm_[ss] * e;
+                    st[ss * kB2StagePitch] = e;
+                    zout = X + dprev;
+                    dprev = D;
+                    yprev = Y;
+                    if (t == 0) {
+                        if (ROLL) {
+                            // lane 0 is 31 columns behind the leading edge: until it rolls over it
+                            // still writes the boundary row of the previous segment
+                            int bi = posS + ss - 31;
+                            bi += (bi < 0) ? M : 0;
+                            bnd[bi] = zout;
+                        } else {
+                            bw[ss] = zout;
+                        }
+                    }
+                }
+            };
+            if (simple_roll) body(std::true_type{});
+            else body(std::false_type{});
         } else {
             // ---- general block: two segments, start / end of the sequence, partial strips.
             // Q of cells outside the lattice was never written (arbitrary bits): products

@@ -29,6 +29,8 @@
 //     ahead of the reader (lane 0 of chain 0) of the same column.
 // Requirements (checked by the host): no per-pair lengths, M % 16 == 0, M >= 32 NCH + 32.
 #pragma once
+#include <type_traits>
+
 #include "softdp_fwd2.cuh"
 
 namespace b200dp {
@@ -181,47 +183,82 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
 #pragma unroll
         for (int c = 0; c < NCH; ++c) part[c] = 0.f;
 
-        if (plain && Lvalid && fullL) {
-            // ---- steady block: one segment, every row inside the lattice ------------------
-            const int pairL = pair_of(idxL);
-            float* qb = p.Q + (long long)pairL * PS + (long long)(passL * NCH) * SS + (long long)posL * kStepFloats + t;
-            float* bw = bnd + (posL - 32 * NCH + 1);
-            float th_[NCH][16], a_[NCH][16], bv_[16];
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-                for (int ss = 0; ss < 16; ++ss) {
-                    const float* tb = reinterpret_cast<const float*>(((tp <= ss) ? sB : sA) + c * 4096);
-                    th_[c][ss] = tb[ss];
-                    a_[c][ss] = tb[ss + 256];
-                }
-            }
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                const float4 b4 = reinterpret_cast<const float4*>(br)[q4];
-                bv_[4 * q4] = b4.x;
-                bv_[4 * q4 + 1] = b4.y;
-                bv_[4 * q4 + 2] = b4.z;
-                bv_[4 * q4 + 3] = b4.w;
-            }
-#pragma unroll
-            for (int ss = 0; ss < 16; ++ss) {
-                float r[NCH];
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) r[c] = __shfl_sync(kFull, h[c], rot);
+        // roll-over inside one pair (single chain), both strips complete: the steady step plus
+        // the row-start resets; no pair boundary, no partial rows, no Vt (sw.py's column 1 is
+        // met at the roll-over and stays on the general path)
+        const bool simple_roll = (NCH == 1) && !SWM && !plain && Lvalid && passL > 0 && fullL;
+        if ((plain && Lvalid && fullL) || simple_roll) {
+            // ---- steady block (ROLL = false): one segment, every row inside the lattice;
+            // simple roll-over block (ROLL = true): lanes t < ss + posL already in segment L ----
+            auto body = [&](auto roll_tag) {
+                constexpr bool ROLL = decltype(roll_tag)::value;
+                const int pairL = pair_of(idxL);
+                // (with one chain the storage of segment T continues into segment L: one pointer)
+                float* qb = p.Q + (long long)pairL * PS + (long long)(passL * NCH) * SS + (long long)posL * kStepFloats + t;
+                float* bw = bnd + (posL - 32 * NCH + 1);
+                const int roll0 = t - posL;                   // ROLL: step at which the lane enters L
+                float th_[NCH][16], a_[NCH][16], bv_[16];
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
-                    const float hup = (t == 0) ? (c == 0 ? bv_[ss] : r[c > 0 ? c - 1 : 0]) : r[c];
-                    // chain c: strip passL*NCH + c, wavefront step posL + ss - 32 c of that strip
-                    float* qp = qb + (long long)c * (SS - 32 * kStepFloats) + ss * kStepFloats;
-                    // sw.py: row 1 (lane 0 of the pair's first strip) is below the origin -- V = 0, Q = 0
-                    // (column 1 is always met in a roll-over block, i.e. in the general path)
-                    const bool live = !(SWM && c == 0 && t == 0 && passL == 0);
-                    h[c] = fwd2_step<false, SWM, DBG>(th_[c][ss], a_[c][ss], hup, v[c], qp, true, live);
-                    part[c] += h[c];
+#pragma unroll
+                    for (int ss = 0; ss < 16; ++ss) {
+                        const float* tb = reinterpret_cast<const float*>(((tp <= ss) ? sB : sA) + c * 4096);
+                        th_[c][ss] = tb[ss];
+                        a_[c][ss] = tb[ss + 256];
+                    }
                 }
-                if (t == 31) bw[ss] = h[NCH - 1];
-            }
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 b4 = reinterpret_cast<const float4*>(br)[q4];
+                    bv_[4 * q4] = b4.x;
+                    bv_[4 * q4 + 1] = b4.y;
+                    bv_[4 * q4 + 2] = b4.z;
+                    bv_[4 * q4 + 3] = b4.w;
+                }
+#pragma unroll
+                for (int ss = 0; ss < 16; ++ss) {
+                    float r[NCH];
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) r[c] = __shfl_sync(kFull, h[c], rot);
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const float hup = (t == 0) ? (c == 0 ? bv_[ss] : r[c > 0 ? c - 1 : 0]) : r[c];
+                        if (ROLL) {
+                            // first column of the lane's new row: V[i, 0] = 0, a new row sum
+                            const bool at = ss == roll0;
+                            v[c] = at ? 0.f : v[c];
+                            part[c] = at ? 0.f : part[c];
+                        }
+                        // chain c: strip passL*NCH + c, wavefront step posL + ss - 32 c of that strip
+                        float* qp = qb + (long long)c * (SS - 32 * kStepFloats) + ss * kStepFloats;
+                        // sw.py: row 1 (lane 0 of the pair's first strip) is below the origin -- V = 0, Q = 0
+                        // (column 1 is always met in a roll-over block, i.e. in the general path)
+                        const bool live = !(SWM && c == 0 && t == 0 && passL == 0);
+                        h[c] = fwd2_step<false, SWM, DBG>(th_[c][ss], a_[c][ss], hup, v[c], qp, true, live);
+                        part[c] += h[c];
+                    }
+                    if (t == 31) {
+                        if (ROLL) {
+                            // lane 31 is 31 columns behind the leading edge: until it rolls over it
+                            // still writes the boundary row of the previous segment
+                            int bi = posL + ss - 31;
+                            bi += (bi < 0) ? M : 0;
+                            bnd[bi] = h[NCH - 1];
+                        } else {
+                            bw[ss] = h[NCH - 1];
+                        }
+                    }
+                }
+                if (ROLL) {
+                    // a lane that finished a row (not the pair's last: no Vt here) starts a new row sum
+                    if (roll0 >= 0 && roll0 < 16) {
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) acc_hi[c] = acc_lo[c] = 0.f;
+                    }
+                }
+            };
+            if (simple_roll) body(std::true_type{});
+            else body(std::false_type{});
         } else {
             // ---- general block: lanes may sit in two segments (T = the older one, L), be
             // before the start / past the end of the CTA's sequence, or below the lattice ----
