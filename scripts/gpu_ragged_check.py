@@ -1,3 +1,7 @@
+#!/usr/bin/env python
+"""Forward + backward on a ragged batch (Zipf lengths, multiples of 64) with a device
+synchronisation after each pass: the quick check for the hand-off kernels on many short
+pairs per CTA.  usage: python scripts/gpu_ragged_check.py B kmax seed [flags]"""
 import os, sys, numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
