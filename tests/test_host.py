@@ -133,3 +133,46 @@ def test_two_rank_gloo_sharding(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_state_string_matches_revstate_f():
+    """deepblast/dataset/utils.py:32-38 (revstate_f) + trainer.py:86-87."""
+    from deepblast_b200.align import state_string
+    decoded = [(0, 0, 1), (1, 0, 0), (1, 1, 2), (2, 2, 1)]
+    assert state_string(decoded) == ":12:"
+    assert state_string([]) == ""
+
+
+def test_new_entry_points_fail_loudly_without_a_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only behaviour")
+    from deepblast_b200 import ops
+    from deepblast_b200.losses import MatrixCrossEntropy
+    t = torch.rand(2, 8, 8)
+    with pytest.raises(RuntimeError):
+        ops.decode_host(t, t, "nw")
+    with pytest.raises(RuntimeError):
+        MatrixCrossEntropy()(t, t, [8, 8], [8, 8], torch.ones_like(t))
+    with pytest.raises(TypeError):
+        ops.decode_host(t.double(), t.double(), "nw")
+
+
+def test_host_entry_argument_errors():
+    """b200dp_decode_host / b200dp_mxent_* reject bad arguments before touching the device."""
+    from deepblast_b200 import _lib
+    L = _lib.lib()
+    assert L.b200dp_decode_host_workspace(256, 256, 64) > 3 * 64 * (2 * 256 * 256 * 4)
+    assert L.b200dp_decode_host_workspace(0, 256, 64) == 0
+    assert L.b200dp_decode_host(None, None, None, None, None, 4, 8, 8, 0, 2, None, 0, 0, None) != 0
+    assert b"null pointer" in L.b200dp_last_error()
+    assert L.b200dp_decode_host(None, None, None, None, None, 4, 8, 8, 7, 2, None, 0, 0, None) != 0
+    assert b"bad mode" in L.b200dp_last_error()
+    assert L.b200dp_mxent_fwd(None, None, 0, 0, None, None, None, 4, 8, 8, None, None, None) != 0
+    assert b"null pointer" in L.b200dp_last_error()
+    assert L.b200dp_mxent_fwd(None, None, 0, 0, None, None, None, 0, 8, 8, None, None, None) == 0     # empty batch
+
+
+def test_bench_affinity_helper_never_raises():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert isinstance(bench.bind_to_gpu_numa_node(0), str)
