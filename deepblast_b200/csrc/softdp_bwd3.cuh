@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
         const bool sw_dead = SWM && kbL == 0 && t == 0;       // row 1 (sw.py: i >= 2): E = 0, nothing pushed
 
         // roll-over inside one pair, both strips complete: the steady step plus the row-start
-        // resets (no tail tile, no partial rows, no seed; sw.py's column 1 stays on the general path)
-        const bool simple_roll = !SWM && !plain && Lvalid && kL > 0 && (kbL + 2) * kTile <= N;
+        // resets (no tail tile, no partial rows, no seed)
+        const bool simple_roll = !plain && Lvalid && kL > 0 && (kbL + 2) * kTile <= N;
         if ((plain && Lvalid && fullL && !sw_special) || simple_roll) {
             // ---- steady block (ROLL = false) / simple roll-over block (ROLL = true) ----------
             auto body = [&](auto roll_tag) {
@@ -254,7 +254,13 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
                         dprev = at ? 0.f : dprev;
                     }
                     float e = zin + yprev;
-                    if (SWM) e = sw_dead ? 0.f : e;           // the marks are finite: 0 * mark = 0
+                    if (SWM) {
+                        // sw.py sweeps i, j >= 2: row 1 (lane 0 of the top strip, once it is in L) and
+                        // column 1 (the step before a lane starts its new row) hold E = 0 and push
+                        // nothing; their Q marks are finite, 0 * mark = 0
+                        const bool dead = ROLL ? ((sw_dead && ss >= roll) || ss == roll - 1) : sw_dead;
+                        e = dead ? 0.f : e;
+                    }
                     const float X = qx_[ss] * e;
                     const float Y = qy_[ss] * e;
                     const float D = qm_[ss] * e;

@@ -184,9 +184,8 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
         for (int c = 0; c < NCH; ++c) part[c] = 0.f;
 
         // roll-over inside one pair (single chain), both strips complete: the steady step plus
-        // the row-start resets; no pair boundary, no partial rows, no Vt (sw.py's column 1 is
-        // met at the roll-over and stays on the general path)
-        const bool simple_roll = (NCH == 1) && !SWM && !plain && Lvalid && passL > 0 && fullL;
+        // the row-start resets; no pair boundary, no partial rows, no Vt
+        const bool simple_roll = (NCH == 1) && !plain && Lvalid && passL > 0 && fullL;
         if ((plain && Lvalid && fullL) || simple_roll) {
             // ---- steady block (ROLL = false): one segment, every row inside the lattice;
             // simple roll-over block (ROLL = true): lanes t < ss + posL already in segment L ----
@@ -223,9 +222,10 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
                         const float hup = (t == 0) ? (c == 0 ? bv_[ss] : r[c > 0 ? c - 1 : 0]) : r[c];
+                        bool at = false;
                         if (ROLL) {
                             // first column of the lane's new row: V[i, 0] = 0, a new row sum
-                            const bool at = ss == roll0;
+                            at = ss == roll0;
                             v[c] = at ? 0.f : v[c];
                             part[c] = at ? 0.f : part[c];
                         }
@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
                         float* qp = qb + (long long)c * (SS - 32 * kStepFloats) + ss * kStepFloats;
                         // sw.py: row 1 (lane 0 of the pair's first strip) is below the origin -- V = 0, Q = 0
                         // (column 1 is always met in a roll-over block, i.e. in the general path)
-                        const bool live = !(SWM && c == 0 && t == 0 && passL == 0);
+                        // and column 1 (the first column of a new row, ROLL only) as well
+                        const bool live = !(SWM && ((c == 0 && t == 0 && passL == 0) || at));
                         h[c] = fwd2_step<false, SWM, DBG>(th_[c][ss], a_[c][ss], hup, v[c], qp, true, live);
                         part[c] += h[c];
                     }
