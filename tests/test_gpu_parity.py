@@ -390,3 +390,24 @@ def test_ragged_many_pairs_per_cta_handoff(ops, kern):
         E_o = O.backward_pass(np.ones(1, np.float32), Q_o, "nw")
         np.testing.assert_allclose(res[8][0][b].item(), Vt_o[0], rtol=1e-6)
         np.testing.assert_allclose(res[8][1][b, 1:n + 1, 1:m + 1].cpu().numpy(), E_o[0, 1:-1, 1:-1], rtol=0, atol=ATOL_QE * 2)
+
+
+def test_c4_shape_on_the_chained_kernels(ops):
+    """BASELINE configs[3] per-GPU lattice (512 x 512) at the smallest batch the chained
+    kernels take by default (2 pairs per SM): oracle on a sample, size-independent properties on all."""
+    B, N, M = 2 * torch.cuda.get_device_properties(0).multi_processor_count + 4, 512, 512
+    g = torch.Generator(device=dev()).manual_seed(4)
+    th = torch.rand(B, N, M, generator=g, device=dev())
+    a = -torch.rand(B, N, M, generator=g, device=dev())
+    Vt, Q = ops.forward_pass(th, a, "nw")
+    Et = torch.linspace(0.5, 1.5, B, device=dev())
+    E = ops.backward_pass(Et, Q, "nw", N=N)
+    assert torch.allclose(E[:, N, M], Et) and (E >= 0).all()
+    src = E[:, 1, 1:M + 1].sum(-1) + E[:, 2:N + 1, 1].sum(-1)          # all flow crosses row 1 / column 1
+    assert (src >= Et * (1.0 - 1e-3)).all()
+    idx = [0, B // 2, B - 1]
+    Vt_o, Q_o = O.forward_pass(th[idx].cpu().numpy(), a[idx].cpu().numpy(), "nw")
+    E_o = O.backward_pass(Et[idx].cpu().numpy(), Q_o, "nw")
+    np.testing.assert_allclose(Vt[idx].cpu().numpy(), Vt_o, rtol=1e-6)
+    np.testing.assert_allclose(ops.q_to_reference(Q, N)[idx].cpu().numpy(), Q_o, rtol=0, atol=ATOL_QE)
+    np.testing.assert_allclose(E[idx].cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
