@@ -63,6 +63,9 @@ def zipf_lengths(B, rng):
     return 64 * rng.choice(k, size=B, p=pk), 64 * rng.choice(k, size=B, p=pk)
 
 
+_ALL_CPUS = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+
+
 def bind_to_gpu_numa_node(index):
     """Pin this process (and so the pinned host buffers it first-touches) to the CPU cores
     NVML reports as local to GPU `index`: host<->device copies then stay on the GPU's own
@@ -140,7 +143,7 @@ def cpu_port_throughput(mode, N, M, xlen=None, ylen=None, target_s=12.0, seed=2)
     """Oracle port (oracle/softdp_oracle.c, fp64, OpenMP over pairs) on a bounded sample
     of the same workload.  Returns (cells/s, cores, sample description, seconds)."""
     from oracle import softdp as O
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     rng = np.random.default_rng(seed)
 
     def run(Bs):
@@ -420,6 +423,8 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
+            if _ALL_CPUS:
+                os.sched_setaffinity(0, _ALL_CPUS)        # the CPU baseline gets every host core again
             xl = None if xlen is None else xlen.cpu().numpy()
             yl = None if ylen is None else ylen.cpu().numpy()
             v, cores, sample, _ = cpu_port_throughput(mode, N, M, xl, yl, target_s=args.cpu_seconds)
