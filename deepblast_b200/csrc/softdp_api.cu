@@ -410,6 +410,9 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
     p.theta = theta;
     p.A = A;
     p.Q = Q;
+    p.Qin = nullptr;
+    p.has_za = 0;
+    p.has_e = 0;
     p.Vt = Vt;
     p.d = PairDims{xlen, ylen, B, N, M};
     p.ql = q_layout(N, M);
@@ -510,6 +513,7 @@ int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E, c
     p.Et = Et;
     p.et_stride = et_stride;
     p.Q = Q;
+    p.QdE = nullptr;
     p.E = E;
     p.d = PairDims{xlen, ylen, B, N, M};
     p.ql = q_layout(N, M);
@@ -632,6 +636,105 @@ int b200dp_traceback(const float* grad, long long sb, long long si, long long sj
     softdp_traceback_kernel<<<(B + threads - 1) / threads, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "b200dp_traceback launch");
+    return 0;
+}
+
+// ---- chained adjoint pair (double backward on large batches of equal-size lattices) ----------
+static bool adj3_shape_ok(int B, int N, int M) {
+    if (const char* e = getenv("B200DP_V3")) if (atoi(e) == 0) return false;
+    DevInfo di;
+    if (!dev_info(di)) return false;
+    int minB = 2 * di.sms;
+    if (const char* e = getenv("B200DP_V3MIN")) minB = atoi(e);
+    return B >= minB && N >= kTile && M >= 64 && M % 32 == 0 && get_encode() != nullptr;
+}
+
+static int chained_grid(int B, size_t smem, int& grid) {
+    DevInfo di;
+    if (!dev_info(di)) return -1;
+    if (smem > (size_t)di.smem_optin) return -1;
+    int per_sm = (int)((size_t)di.smem_per_sm / (smem + 1024));
+    if (per_sm > 32) per_sm = 32;
+    if (per_sm < 1) return -1;
+    const long long resident = (long long)di.sms * per_sm;
+    const long long rounds = (B + resident - 1) / resident;
+    grid = (int)((B + rounds - 1) / rounds);
+    if (const char* e = getenv("B200DP_CTAS")) if (atoi(e) > 0) grid = atoi(e);
+    return (int)rounds;
+}
+
+int b200dp_adj3_applicable(int B, int N, int M) { return (B > 0 && N > 0 && M > 0 && adj3_shape_ok(B, N, M)) ? 1 : 0; }
+
+int b200dp_adj_fwd3(const float* Q, const float* Zt, const float* ZA, const float* E, float* Vtd, float* QdE, int B,
+                    int N, int M, int flags, void* stream) {
+    if (int rc = check_common("b200dp_adj_fwd3", B, N, M)) return rc;
+    if (B == 0) return 0;
+    if (!Q || !Zt || !Vtd || !QdE) return fail(-1, "b200dp_adj_fwd3: null pointer");
+    if (!adj3_shape_ok(B, N, M)) return fail(-4, "b200dp_adj_fwd3: shape not taken by the chained kernels (b200dp_adj3_applicable)");
+    if (!aligned(Q, 16) || !aligned(QdE, 16) || !aligned(Zt, 16) || (ZA && !aligned(ZA, 16)) || (E && !aligned(E, 16)))
+        return fail(-1, "b200dp_adj_fwd3: pointers must be 16-byte aligned");
+    CUtensorMap tmZ, tmA, tmE;
+    if (!encode_row_map(&tmZ, Zt, B, N, M, kG) || !encode_row_map(&tmA, ZA ? ZA : Zt, B, N, M, kG) ||
+        !encode_row_map(&tmE, E ? E : Zt, B, N, M, kG))
+        return fail(-2, "b200dp_adj_fwd3: cuTensorMapEncodeTiled failed");
+    FwdParams p;
+    p.theta = Zt;
+    p.A = ZA;
+    p.Q = QdE;
+    p.Qin = Q;
+    p.Vt = Vtd;
+    p.d = PairDims{nullptr, nullptr, B, N, M};
+    p.ql = q_layout(N, M);
+    p.i0 = 1;
+    p.flags = flags;
+    p.has_za = ZA ? 1 : 0;
+    p.has_e = E ? 1 : 0;
+    p.pf_tiles = 0;
+    p.pf_dist = 0;
+    const size_t smem = fwd3_smem_bytes<1, 3, true>(M);
+    int grid = 0;
+    if (chained_grid(B, smem, grid) < 0) return fail(-3, "b200dp_adj_fwd3: M too large for shared memory");
+    auto kern = softdp_fwd3_kernel<false, 1, 3, 0, true>;
+    if (int rc = set_smem(kern, smem, "b200dp_adj_fwd3")) return rc;
+    kern<<<grid, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmZ, tmA, tmE, tmE, p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "b200dp_adj_fwd3 launch");
+    return 0;
+}
+
+int b200dp_adj_bwd3(const float* Q, const float* QdE, float* Ed, int B, int N, int M, int flags, void* stream) {
+    if (int rc = check_common("b200dp_adj_bwd3", B, N, M)) return rc;
+    if (B == 0) return 0;
+    if (!Q || !QdE || !Ed) return fail(-1, "b200dp_adj_bwd3: null pointer");
+    if (!adj3_shape_ok(B, N, M)) return fail(-4, "b200dp_adj_bwd3: shape not taken by the chained kernels (b200dp_adj3_applicable)");
+    if (!aligned(Q, 16) || !aligned(QdE, 16)) return fail(-1, "b200dp_adj_bwd3: Q / QdE storage must be 16-byte aligned");
+    BwdParams p;
+    p.Et = nullptr;
+    p.et_stride = 0;
+    p.Q = Q;
+    p.QdE = QdE;
+    p.E = Ed;
+    p.d = PairDims{nullptr, nullptr, B, N, M};
+    p.ql = q_layout(N, M);
+    p.i0 = 1;
+    p.flags = flags;
+    // three Q + QdE slots unless the smaller ring saves a whole round of CTAs
+    int g3 = 0, g2 = 0;
+    const size_t s3 = bwd3_smem_bytes<3, true>(M), s2 = bwd3_smem_bytes<2, true>(M);
+    const int r3 = chained_grid(B, s3, g3), r2 = chained_grid(B, s2, g2);
+    if (r2 < 0) return fail(-3, "b200dp_adj_bwd3: M too large for shared memory");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (r3 > 0 && r3 <= r2) {
+        auto kern = softdp_bwd3_kernel<false, 3, true>;
+        if (int rc = set_smem(kern, s3, "b200dp_adj_bwd3")) return rc;
+        kern<<<g3, 32, s3, st>>>(p);
+    } else {
+        auto kern = softdp_bwd3_kernel<false, 2, true>;
+        if (int rc = set_smem(kern, s2, "b200dp_adj_bwd3")) return rc;
+        kern<<<g2, 32, s2, st>>>(p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "b200dp_adj_bwd3 launch");
     return 0;
 }
 

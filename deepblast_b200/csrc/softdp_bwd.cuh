@@ -20,7 +20,8 @@ struct BwdParams {
     const float* Et;      // [B], stride et_stride (0 for an expanded scalar)
     long long et_stride;
     const float* Q;       // strip-major storage base
-    float* E;             // [B, N+2, M+2] row-major
+    const float* QdE;     // adjoint backward only (softdp_bwd3_kernel<.., ADJ>): strip-major Qd * E
+    float* E;             // [B, N+2, M+2] row-major (adjoint backward: Ed)
     PairDims d;
     QLayout ql;
     int i0;

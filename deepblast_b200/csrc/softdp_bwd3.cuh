@@ -27,9 +27,17 @@ namespace b200dp {
 
 constexpr int kB3StageBytes = ((kB2StageFloats * 4 + 127) / 128) * 128;
 
-template <int RING>
+// ADJ: the same sweep as the ADJOINT backward pass (nw.py:251-267, replaces nw_cuda.py:142-165):
+//   Ed[i,j] = sum over the three successors of ( Qd E + Q Ed ), push form: the cell (i,j),
+//   once ed = Ed[i,j] is known, hands X = Qd_x E + Q_x ed (and likewise D, Y) to its
+//   predecessors.  The products Qd[i,j,:] * E[i,j] are formed by the adjoint FORWARD sweep
+//   (softdp_adj3.cuh), which has E at hand in stream order, and arrive here as a second
+//   strip-major stream (two states, the m state is -(x + y)) next to Q: one more 4 KB bulk
+//   copy per tile and three FFMAs instead of FMULs per step.  No seed (Ed[N,M] = 0 + pushes),
+//   all borders zero; cells whose Q carries the zero mark push nothing.
+template <int RING, bool ADJ = false>
 __host__ __device__ inline size_t bwd3_smem_bytes(int M) {
-    size_t b = (size_t)RING * kDiagElems * 4 + kB3StageBytes;
+    size_t b = (size_t)RING * kDiagElems * (ADJ ? 2 : 1) * 4 + kB3StageBytes;
     b += (size_t)RING * 8;
     b = (b + 15) & ~(size_t)15;
     b += (size_t)M * 4;                            // boundary row
@@ -67,8 +75,10 @@ __device__ __forceinline__ void bwd3_drain_tile(const float* __restrict__ stage,
     }
 }
 
-template <bool SWM, int RING>
+template <bool SWM, int RING, bool ADJ = false>
 __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
+    static_assert(!(SWM && ADJ), "the adjoint sweeps cover the full range (sw.py:150-151,199-201)");
+    constexpr int kSlotElems = kDiagElems * (ADJ ? 2 : 1);      // [Q tile | QdE tile]
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int t = threadIdx.x, u = 31 - t;
     const int N = p.d.N, M = p.d.M, B = p.d.B;
@@ -76,8 +86,8 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
     const int TA = (K * M) >> 4;                  // 16-step blocks (= main Q tiles) per pair
 
     float* qring = reinterpret_cast<float*>(smem_raw);
-    float* stage = qring + RING * kDiagElems;
-    size_t off = (size_t)RING * kDiagElems * 4 + kB3StageBytes;
+    float* stage = qring + RING * kSlotElems;
+    size_t off = (size_t)RING * kSlotElems * 4 + kB3StageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + off);
     off = (off + (size_t)RING * 8 + 15) & ~(size_t)15;
     float* bnd = reinterpret_cast<float*>(smem_raw + off);
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
     auto wait_tile = [&]() -> const float* {
         mbar_wait(&bars[wslot], (phases >> wslot) & 1u);
         phases ^= 1u << wslot;
-        const float* s = qring + wslot * kDiagElems;
+        const float* s = qring + wslot * kSlotElems;
         wslot = (wslot + 1 == RING) ? 0u : wslot + 1;
         return s;
     };
@@ -167,7 +177,7 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
                 if (kb == 0)
                     for (int col = t; col < M + 2; col += 32) Eb[col] = 0.f;
                 if (d_k == 0) {
-                    const float et = p.Et[(long long)pair * p.et_stride];
+                    const float et = ADJ ? 0.f : p.Et[(long long)pair * p.et_stride];
                     for (int col = t; col < M + 2; col += 32)
                         Eb[(long long)(N + 1) * (M + 2) + col] = (col == M + 1) ? et : 0.f;
                 }
@@ -186,8 +196,12 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
         {
             int pr, tile;
             while (iss_cnt - con_cnt < RING && next_tile(pr, tile)) {
-                q_tile_load<true>(qring + islot * kDiagElems, &bars[islot], p.Q + (long long)pair_of(pr) * PS,
-                                  K * M + 15 - kDiagRows * tile, t);
+                const long long po = (long long)pair_of(pr) * PS;
+                q_tile_load<true>(qring + islot * kSlotElems, &bars[islot], p.Q + po, K * M + 15 - kDiagRows * tile, t,
+                                  ADJ ? 2 : 1);
+                if (ADJ)
+                    q_tile_load<true>(qring + islot * kSlotElems + kDiagElems, &bars[islot], p.QdE + po,
+                                      K * M + 15 - kDiagRows * tile, t, 0);
                 islot = (islot + 1 == RING) ? 0u : islot + 1;
                 iss_cnt++;
             }
@@ -236,13 +250,28 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
                 // stores inside the loop may alias the Q ring as far as the compiler knows, so loads
                 // left in the loop would be serialised behind them, one shared-memory latency per step
                 float qx_[16], qy_[16], qm_[16];
+                float px_[ADJ ? 16 : 1], py_[ADJ ? 16 : 1], pm_[ADJ ? 16 : 1];
 #pragma unroll
                 for (int ss = 0; ss < 16; ++ss) {
                     qx_[ss] = qt[(15 - ss) * kStepFloats];
                     qy_[ss] = qt[(15 - ss) * kStepFloats + kQY];
+                    if (ADJ) {
+                        px_[ss] = qt[kDiagElems + (15 - ss) * kStepFloats];
+                        py_[ss] = qt[kDiagElems + (15 - ss) * kStepFloats + kQY];
+                    }
                 }
 #pragma unroll
-                for (int ss = 0; ss < 16; ++ss) qm_[ss] = (1.f - qx_[ss]) - qy_[ss];   // >= 0 by the forward's clamp
+                for (int ss = 0; ss < 16; ++ss) {
+                    qm_[ss] = (1.f - qx_[ss]) - qy_[ss];      // >= 0 by the forward's clamp
+                    if (ADJ) {
+                        // a marked cell (Q == 0, sw.py first row / column) pushes nothing
+                        const bool live = qx_[ss] >= 0.f;
+                        qx_[ss] = live ? qx_[ss] : 0.f;
+                        qy_[ss] = live ? qy_[ss] : 0.f;
+                        qm_[ss] = live ? qm_[ss] : 0.f;
+                        pm_[ss] = -(px_[ss] + py_[ss]);       // Qd sums to 0 over the states
+                    }
+                }
 #pragma unroll
                 for (int ss = 0; ss < 16; ++ss) {
                     float zin = __shfl_down_sync(kFull, zout, 1);
@@ -261,9 +290,9 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
                         const bool dead = ROLL ? ((sw_dead && ss >= roll) || ss == roll - 1) : sw_dead;
                         e = dead ? 0.f : e;
                     }
-                    const float X = qx_[ss] * e;
-                    const float Y = qy_[ss] * e;
-                    const float D = qm_[ss] * e;
+                    const float X = ADJ ? fmaf(qx_[ss], e, px_[ss]) : qx_[ss] * e;
+                    const float Y = ADJ ? fmaf(qy_[ss], e, py_[ss]) : qy_[ss] * e;
+                    const float D = ADJ ? fmaf(qm_[ss], e, pm_[ss]) : qm_[ss] * e;
                     st[ss * kB2StagePitch] = e;
                     zout = X + dprev;
                     dprev = D;
@@ -293,7 +322,7 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
             const bool okL = Lvalid && kbL * kTile + t < N;
             const bool okT = Tvalid && kbT * kTile + t < N;
             const bool seedL = Lvalid && kL == 0 && t == tlast;
-            const float etL = Lvalid ? p.Et[(long long)pair_of(idxL) * p.et_stride] : 0.f;
+            const float etL = (Lvalid && !ADJ) ? p.Et[(long long)pair_of(idxL) * p.et_stride] : 0.f;
             const int shat = 16 * a;                            // local step of the leading edge in pair idxL
 #pragma unroll 4
             for (int ss = 0; ss < 16; ++ss) {
@@ -305,7 +334,7 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
                 dprev = at ? 0.f : dprev;
                 const bool ok = inL ? okL : okT;
                 float e = zin + yprev;
-                if (at && seedL) e = etL;                       // E[N, M] = Et  (nw.py:125-127)
+                if (!ADJ && at && seedL) e = etL;               // E[N, M] = Et  (nw.py:125-127)
                 bool comp = ok;
                 if (SWM) {
                     const int o = posS + ss - u + (inL ? 0 : M);      // columns swept in this row so far
@@ -315,9 +344,18 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
                 e = comp ? e : 0.f;
                 const float* qt = ((has_tail && u > shat + ss) ? qtail : qmain) + t + (15 - ss) * kStepFloats;
                 const float qx = qt[0], qy = qt[kQY];
-                const float X = comp ? qx * e : 0.f;
-                const float Y = comp ? qy * e : 0.f;
-                const float D = comp ? ((1.f - qx) - qy) * e : 0.f;
+                float X, Y, D;
+                if (ADJ) {
+                    const bool live = comp && qx >= 0.f;        // inside the lattice and not a marked cell
+                    const float px = qt[kDiagElems], py = qt[kDiagElems + kQY];
+                    X = live ? fmaf(qx, e, px) : 0.f;
+                    Y = live ? fmaf(qy, e, py) : 0.f;
+                    D = live ? fmaf((1.f - qx) - qy, e, -(px + py)) : 0.f;
+                } else {
+                    X = comp ? qx * e : 0.f;
+                    Y = comp ? qy * e : 0.f;
+                    D = comp ? ((1.f - qx) - qy) * e : 0.f;
+                }
                 st[ss * kB2StagePitch] = e;
                 zout = X + dprev;
                 dprev = D;

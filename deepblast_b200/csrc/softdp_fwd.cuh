@@ -23,6 +23,8 @@ struct FwdParams {
     QLayout ql;
     int i0;               // 1 = Needleman-Wunsch, 2 = "Smith-Waterman" (sw.py:54-55)
     int flags;
+    const float* Qin;     // softdp_fwd3 ADJ (adjoint forward): the forward's Q; `Q` is then the output Qd (* E)
+    int has_za, has_e;    // ... ADJ: ZA / E operands present (else 0 / 1)
     int pf_tiles;         // softdp_fwd3: L2 prefetch box width in 16-column tiles (0 = off)
     int pf_dist;          // ... issued this many tiles ahead of the leading TMA tile
 };

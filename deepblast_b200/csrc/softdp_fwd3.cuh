@@ -35,9 +35,24 @@
 
 namespace b200dp {
 
-template <int NCH, int RING>
+// ADJ: the same chained sweep as the ADJOINT forward pass (nw.py:178-199, replaces
+// nw_cuda.py:105-139) in difference form:
+//   dx = za + hd[i-1,j], dy = za + vd[i,j-1]        (w_x - w_m, w_y - w_m of nw.py:188-192)
+//   g  = q_x dx + q_y dy                             (sum_s q_s w_s - w_m; Q sums to 1)
+//   Vd[i,j] - Vd[i-1,j-1] = ztheta + g,   Qd_x = q_x (dx - g),  Qd_y = q_y (dy - g)
+// Operands per 16x16 box: ztheta, ZA (optional), E (optional) -- contiguous [B, N, M]
+// tensors through TMA exactly like theta / A; the forward's Q arrives as a strip-major
+// stream of 4 KB bulk-TMA tiles (main tile of the block, plus the tail tile of the previous
+// pair in the two blocks after a pair boundary, as in softdp_bwd3.cuh); the output stream
+// holds Qd * E (what the adjoint backward sweep consumes), or Qd when E is absent.  A cell
+// whose Q carries the zero mark has Vd = ztheta (its diagonal predecessor is on the zero
+// border) and Qd = 0.  Vtd = Vd[N, M] = sum_j hd[N, j].
+constexpr int kAdj3QRing = 3;
+
+template <int NCH, int RING, bool ADJ = false>
 __host__ __device__ inline size_t fwd3_smem_bytes(int M) {
-    size_t b = (size_t)RING * NCH * 4096;          // [RING][2 NCH groups][theta, A][16][16] fp32
+    size_t b = (size_t)RING * NCH * (ADJ ? 6144 : 4096);   // [RING][2 NCH groups][theta, A (, E)][16][16] fp32
+    if (ADJ) b += (size_t)kAdj3QRing * kDiagElems * 4 + (size_t)kAdj3QRing * 8;
     b += (size_t)RING * 8;                         // mbarriers
     b = (b + 15) & ~(size_t)15;
     b += (size_t)M * 4;                            // boundary row
@@ -45,25 +60,62 @@ __host__ __device__ inline size_t fwd3_smem_bytes(int M) {
     return b;
 }
 
-template <bool SWM, int NCH, int RING, int DBG = 0>
+// One step of the adjoint forward sweep (see the ADJ note above); same calling convention
+// as fwd2_step.  e = 1 when the E operand is absent, za = 0 when ZA is absent.
+template <bool EDGE>
+__device__ __forceinline__ float adj3_step(float zt, float za, float e, float qx, float qy, float hup, float& v,
+                                           float* __restrict__ qp, bool store, bool comp) {
+    const bool live = qx >= 0.f;                     // a marked cell: Q == 0
+    qx = live ? qx : 0.f;
+    qy = live ? qy : 0.f;
+    const float dx = za + hup;
+    const float dy = za + v;
+    const float g = fmaf(qx, dx, qy * dy);
+    const float ld = zt + g;
+    float hn = ld - v;
+    float vn = ld - hup;
+    const float qdx = (qx * (dx - g)) * e;           // nw.py:30-43; Qd_m = -(Qd_x + Qd_y) is implied
+    const float qdy = (qy * (dy - g)) * e;
+    if (EDGE) {
+        hn = comp ? hn : 0.f;
+        vn = comp ? vn : 0.f;
+    }
+    if (!EDGE || store) {
+        qp[0] = qdx;
+        qp[kQY] = qdy;
+    }
+    v = vn;
+    return hn;
+}
+
+template <bool SWM, int NCH, int RING, int DBG = 0, bool ADJ = false>
 __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__ CUtensorMap tm_theta,
                                                          const __grid_constant__ CUtensorMap tm_A,
                                                          const __grid_constant__ CUtensorMap tm_pf_theta,
                                                          const __grid_constant__ CUtensorMap tm_pf_A, FwdParams p) {
+    static_assert(!ADJ || (NCH == 1 && !SWM && DBG == 0), "adjoint forward: one chain, full range");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    constexpr int kSlot = NCH * 4096;
+    constexpr int kGroupBytes = ADJ ? 3072 : 2048;       // [theta, A (, E)][16][16] fp32
+    constexpr int kSlot = NCH * 2 * kGroupBytes;
     constexpr int kGroups = 2 * NCH;
+    const CUtensorMap& tm_E = tm_pf_theta;               // ADJ: the third operand travels in the prefetch map's slot
     const int t = threadIdx.x, g = t >> 4, tp = t & 15;
     const int N = p.d.N, M = p.d.M, B = p.d.B;
     const int K = (N + 31) >> 5, P = (K + NCH - 1) / NCH, T16 = M >> 4;
 
     unsigned char* ring = smem_raw;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)RING * kSlot);
-    float* bnd = reinterpret_cast<float*>(smem_raw + (((size_t)RING * kSlot + RING * 8 + 15) & ~(size_t)15));
+    constexpr size_t kQRingBytes = ADJ ? (size_t)kAdj3QRing * kDiagElems * 4 : 0;
+    float* qring = reinterpret_cast<float*>(smem_raw + (size_t)RING * kSlot);          // ADJ: Q tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)RING * kSlot + kQRingBytes);
+    uint64_t* qbars = bars + RING;
+    constexpr size_t kBarBytes = (size_t)(RING + (ADJ ? kAdj3QRing : 0)) * 8;
+    float* bnd = reinterpret_cast<float*>(smem_raw + (((size_t)RING * kSlot + kQRingBytes + kBarBytes + 15) & ~(size_t)15));
     float* zero_row = bnd + M;
 
     if (t == 0) {
         for (int s = 0; s < RING; ++s) mbar_init(&bars[s], 1);
+        if (ADJ)
+            for (int s = 0; s < kAdj3QRing; ++s) mbar_init(&qbars[s], 1);
         tma_prefetch_desc(&tm_theta);
         tma_prefetch_desc(&tm_A);
         if (p.pf_tiles > 0) {
@@ -121,9 +173,10 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
     }
     auto issue_event = [&](int e, unsigned slot) {
         unsigned bytes = 0;
+        const unsigned gbytes = ADJ ? 1024u * (1u + (p.has_za ? 1u : 0u) + (p.has_e ? 1u : 0u)) : 2048u;
 #pragma unroll
         for (int j = 0; j < kGroups; ++j)
-            if (e - j >= 0 && e - j < NT) bytes += 2048u;
+            if (e - j >= 0 && e - j < NT) bytes += gbytes;
         const bool leader = !(DBG & 2) && elect_one();
         if (pf_tiles > 0) pf_step(leader);
         if (leader) mbar_expect_tx(&bars[slot], bytes);
@@ -133,9 +186,10 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
                 if (leader) {
                     const int row0 = (c_pass[j] * NCH + (j >> 1)) * kTile + (j & 1) * kG;
                     const int pair = pair_of(c_idx[j]);
-                    unsigned char* dst = ring + slot * kSlot + j * 2048;
+                    unsigned char* dst = ring + slot * kSlot + j * kGroupBytes;
                     tma_load_3d(dst, &tm_theta, &bars[slot], c_ct[j] * kG, row0, pair);
-                    tma_load_3d(dst + 1024, &tm_A, &bars[slot], c_ct[j] * kG, row0, pair);
+                    if (!ADJ || p.has_za) tma_load_3d(dst + 1024, &tm_A, &bars[slot], c_ct[j] * kG, row0, pair);
+                    if (ADJ && p.has_e) tma_load_3d(dst + 2048, &tm_E, &bars[slot], c_ct[j] * kG, row0, pair);
                 }
                 if (++c_ct[j] == T16) {
                     c_ct[j] = 0;
@@ -156,8 +210,48 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
     int idxT = 0, passT = 0;                        // the segment before it
     const int tlast = (N - 1) & 31, clast = ((N - 1) >> 5) % NCH;
     const int rot = (t + 31) & 31;
-    const int lanebase = g * 2048 + tp * 60;        // group-in-chain, row, -4*tp column skew (bytes)
+    const int lanebase = g * kGroupBytes + tp * 60; // group-in-chain, row, -4*tp column skew (bytes)
     unsigned slotA = 0, slotB = 0;
+
+    // ---- ADJ: the forward's Q as a FIFO of 4 KB tiles (16 lines of the pair's stream).  Block
+    // a = pass * T16 + pos / 16 of pair idx needs main tile a of that pair and, while a < 2 and
+    // idx >= 1, tail tile TA + a of the previous pair (lanes that have not rolled over yet) ------
+    const int TA = P * T16;
+    int iss_idx = 0, iss_a = 0, iss_sub = 0, iss_cnt = 0, con_cnt = 0;
+    unsigned qislot = 0, qwslot = 0, qphases = 0;
+    auto next_tile = [&](int& pr, int& tile) -> bool {
+        for (;;) {
+            if (iss_idx > npairs || (iss_idx == npairs && iss_a >= 2)) return false;
+            if (iss_sub == 0) {
+                iss_sub = 1;
+                if (iss_idx < npairs) {
+                    pr = iss_idx;
+                    tile = iss_a;
+                    return true;
+                }
+            } else {
+                const bool tail = iss_a < 2 && iss_idx >= 1;
+                const int pi = iss_idx - 1, ta = TA + iss_a;
+                iss_sub = 0;
+                if (++iss_a == TA) {
+                    iss_a = 0;
+                    ++iss_idx;
+                }
+                if (tail) {
+                    pr = pi;
+                    tile = ta;
+                    return true;
+                }
+            }
+        }
+    };
+    auto wait_qtile = [&]() -> const float* {
+        mbar_wait(&qbars[qwslot], (qphases >> qwslot) & 1u);
+        qphases ^= 1u << qwslot;
+        const float* sq = qring + qwslot * kDiagElems;
+        qwslot = (qwslot + 1 == kAdj3QRing) ? 0u : qwslot + 1;
+        return sq;
+    };
 
     for (int b = 0; b < NBLK; ++b) {
         __syncwarp();
@@ -172,6 +266,25 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
             phases ^= 1u << wslot;
             slotB = wslot;
             wslot = (wslot + 1 == RING) ? 0u : wslot + 1;
+        }
+        const float* qmain = nullptr;
+        const float* qtail = nullptr;
+        bool has_tail = false;
+        if (ADJ) {
+            int pr, tile;
+            while (iss_cnt - con_cnt < kAdj3QRing && next_tile(pr, tile)) {
+                q_tile_load<true>(qring + qislot * kDiagElems, &qbars[qislot], p.Qin + (long long)pair_of(pr) * PS,
+                                  kDiagRows * tile, t);
+                qislot = (qislot + 1 == kAdj3QRing) ? 0u : qislot + 1;
+                iss_cnt++;
+            }
+            const bool has_main = idxL < npairs;
+            has_tail = passL == 0 && posL < 32 && idxL >= 1;
+            if (has_main) qmain = wait_qtile();
+            if (has_tail) qtail = wait_qtile();
+            if (!has_main) qmain = qtail;
+            if (!has_tail) qtail = qmain;
+            con_cnt += (has_main ? 1 : 0) + (has_tail ? 1 : 0);
         }
         const bool plain = posL >= 32 * NCH;        // every lane of every chain is in segment gL
         const bool Lvalid = gL < G;
@@ -197,13 +310,19 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
                 float* bw = bnd + (posL - 32 * NCH + 1);
                 const int roll0 = t - posL;                   // ROLL: step at which the lane enters L
                 float th_[NCH][16], a_[NCH][16], bv_[16];
+                float e_[ADJ ? 16 : 1], qx_[ADJ ? 16 : 1], qy_[ADJ ? 16 : 1];
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
 #pragma unroll
                     for (int ss = 0; ss < 16; ++ss) {
-                        const float* tb = reinterpret_cast<const float*>(((tp <= ss) ? sB : sA) + c * 4096);
+                        const float* tb = reinterpret_cast<const float*>(((tp <= ss) ? sB : sA) + c * 2 * kGroupBytes);
                         th_[c][ss] = tb[ss];
-                        a_[c][ss] = tb[ss + 256];
+                        a_[c][ss] = (!ADJ || p.has_za) ? tb[ss + 256] : 0.f;
+                        if (ADJ) {
+                            e_[ss] = p.has_e ? tb[ss + 512] : 1.f;
+                            qx_[ss] = qmain[ss * kStepFloats + t];
+                            qy_[ss] = qmain[ss * kStepFloats + kQY + t];
+                        }
                     }
                 }
 #pragma unroll
@@ -235,7 +354,10 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
                         // (column 1 is always met in a roll-over block, i.e. in the general path)
                         // and column 1 (the first column of a new row, ROLL only) as well
                         const bool live = !(SWM && ((c == 0 && t == 0 && passL == 0) || at));
-                        h[c] = fwd2_step<false, SWM, DBG>(th_[c][ss], a_[c][ss], hup, v[c], qp, true, live);
+                        if (ADJ)
+                            h[c] = adj3_step<false>(th_[c][ss], a_[c][ss], e_[ss], qx_[ss], qy_[ss], hup, v[c], qp, true, true);
+                        else
+                            h[c] = fwd2_step<false, SWM, DBG>(th_[c][ss], a_[c][ss], hup, v[c], qp, true, live);
                         part[c] += h[c];
                     }
                     if (t == 31) {
@@ -299,8 +421,15 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
                     bool comp = ok;
                     if (SWM) comp = ok && !at && !(t == 0 && c == 0 && (inL ? passL : pT) == 0);
                     float* qp = (inL ? qL[c] : qT[c]) + ss * kStepFloats;
-                    const float* tb = reinterpret_cast<const float*>(((tp <= ss) ? sB : sA) + c * 4096);
-                    h[c] = fwd2_step<true, SWM, DBG>(tb[ss], tb[ss + 256], hup, v[c], qp, ok, comp);
+                    const float* tb = reinterpret_cast<const float*>(((tp <= ss) ? sB : sA) + c * 2 * kGroupBytes);
+                    if (ADJ) {
+                        // lanes that have not rolled over yet read the previous pair's tail tile
+                        const float* qt = ((has_tail && !inL) ? qtail : qmain) + ss * kStepFloats + t;
+                        h[c] = adj3_step<true>(tb[ss], p.has_za ? tb[ss + 256] : 0.f, p.has_e ? tb[ss + 512] : 1.f,
+                                               ok ? qt[0] : 0.f, ok ? qt[kQY] : 0.f, hup, v[c], qp, ok, comp);
+                    } else {
+                        h[c] = fwd2_step<true, SWM, DBG>(tb[ss], tb[ss + 256], hup, v[c], qp, ok, comp);
+                    }
                     part[c] += h[c];
                 }
                 if (t == 31) {
@@ -314,7 +443,7 @@ __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__
                     // the lane finished a row of segment T in this block:
                     // Vt = V[N, M] = ln 2 * sum_j h[N, j]
                     if (Tvalid && pT == P - 1 && c == clast && t == tlast)
-                        p.Vt[pairT] = (acc_hi[c] + (acc_lo[c] + snap[c])) * kLn2;
+                        p.Vt[pairT] = (acc_hi[c] + (acc_lo[c] + snap[c])) * (ADJ ? 1.f : kLn2);
                     acc_hi[c] = 0.f;
                     acc_lo[c] = 0.f;
                 }

@@ -192,6 +192,39 @@ def adjoint_backward_pass(E, Q, Qd, xlen=None, ylen=None, flags=0):
     return Ed
 
 
+def adjoint_pair_fast(Q, E, Ztheta, ZA=None, N=None, flags=0):
+    """Both adjoint sweeps on the chained kernels (large batches of equal-size lattices):
+    Q (strip-major), E, Ztheta [B,N+2,M+2], ZA [B,N,M] or None (= zeros) -> (Vtd [B],
+    Ed [B,N+2,M+2]), or None when the shape is not taken (use adjoint_forward_pass /
+    adjoint_backward_pass).  The forward sweep multiplies Qd by E on the fly (it reads the
+    interiors of Ztheta and E as contiguous [B,N,M] copies through TMA), so the backward
+    sweep needs Q and that product only."""
+    B, N2, M2 = Ztheta.shape
+    N, M = N2 - 2, M2 - 2
+    if Q.dim() != 5 or not _is_engine_q(Q, N, M) or not Q.is_cuda:
+        return None
+    with torch.cuda.device(Q.device):
+        if not _lib.lib().b200dp_adj3_applicable(B, N, M):
+            return None
+        _check_in("Ztheta", Ztheta, (B, N2, M2))
+        _check_in("E", E, (B, N2, M2))
+        zt = Ztheta.detach()[:, 1:-1, 1:-1].contiguous()
+        e = E.detach()[:, 1:-1, 1:-1].contiguous()
+        za = None
+        if ZA is not None:
+            _check_in("ZA", ZA, (B, N, M))
+            za = ZA.detach().contiguous()
+        QdE = q_empty(B, N, M, Q.device)
+        Vtd = torch.empty(B, dtype=torch.float32, device=Q.device)
+        rc = _lib.lib().b200dp_adj_fwd3(_ptr(Q), _ptr(zt), _ptr(za), _ptr(e), _ptr(Vtd), _ptr(QdE),
+                                        B, N, M, flags, _stream(Q))
+        _lib.check(rc, "b200dp_adj_fwd3")
+        Ed = torch.empty((B, N2, M2), dtype=torch.float32, device=Q.device)
+        rc = _lib.lib().b200dp_adj_bwd3(_ptr(Q), _ptr(QdE), _ptr(Ed), B, N, M, flags, _stream(Q))
+        _lib.check(rc, "b200dp_adj_bwd3")
+    return Vtd, Ed
+
+
 def traceback_batch(grad, xlen=None, ylen=None, variant="cuda"):
     """grad [B,N,M] (any strides) -> list of B lists of (i, j, state) tuples, exactly
     what NeedlemanWunschDecoder.traceback returns per pair (nw.py:401-444 for

@@ -93,6 +93,19 @@ int b200dp_adj_bwd(const float* E, const float* Q, const float* Qd, float* Ed,
                    const int32_t* xlen, const int32_t* ylen, int B, int N, int M,
                    int flags, void* stream);
 
+/* The same pair of sweeps for large batches of equal-size lattices (the double backward of a
+ * training step, trainer.py:154-171 -> nw_cuda.py:243-262), on the chained kernels:
+ *   b200dp_adj3_applicable(B, N, M) -> 1 if they take the shape (else use the pair above);
+ *   b200dp_adj_fwd3: Q, Zt = the INTERIOR of Ztheta as a contiguous [B, N, M] tensor, ZA
+ *     [B, N, M] or NULL (= zeros, the usual case), E interior [B, N, M] or NULL
+ *     -> Vtd [B] and the strip-major stream QdE = Qd * E (Qd itself when E is NULL);
+ *   b200dp_adj_bwd3: Q, QdE -> Ed [B, N+2, M+2] (zero borders). */
+int b200dp_adj3_applicable(int B, int N, int M);
+int b200dp_adj_fwd3(const float* Q, const float* Zt, const float* ZA, const float* E, float* Vtd,
+                    float* QdE, int B, int N, int M, int flags, void* stream);
+int b200dp_adj_bwd3(const float* Q, const float* QdE, float* Ed, int B, int N, int M, int flags,
+                    void* stream);
+
 /* replaces the Python walk NeedlemanWunschDecoder.traceback,
  * deepblast/nw.py:401-444 (variant 0) / deepblast/nw_cuda.py:273-317 (variant 1),
  * batched: grad [B, N, M] with element strides (sb, si, sj) -> out [B, cap, 3]

@@ -411,3 +411,70 @@ def test_c4_shape_on_the_chained_kernels(ops):
     np.testing.assert_allclose(Vt[idx].cpu().numpy(), Vt_o, rtol=1e-6)
     np.testing.assert_allclose(ops.q_to_reference(Q, N)[idx].cpu().numpy(), Q_o, rtol=0, atol=ATOL_QE)
     np.testing.assert_allclose(E[idx].cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
+
+
+ADJ3 = [
+    # mode, B, N, M, CTAs (0 = one per pair), with ZA
+    ("nw", 3, 64, 64, 0, False),
+    ("nw", 13, 96, 128, 3, True),          # several pairs per CTA: tail tiles at the pair boundaries
+    ("nw", 5, 256, 256, 0, False),
+    ("nw", 4, 100, 96, 0, True),           # N % 32 != 0: partial last strip
+    ("sw", 6, 128, 64, 4, False),          # Q with zero marks in row 1 / column 1
+    ("sw", 4, 77, 96, 3, True),
+    ("nw", 2, 512, 1024, 1, False),
+]
+
+
+@pytest.mark.parametrize("mode,B,N,M,ctas,with_za", ADJ3)
+def test_chained_adjoint_pair_vs_oracle(ops, monkeypatch, mode, B, N, M, ctas, with_za):
+    """The chained adjoint sweeps (softdp_fwd3 / softdp_bwd3 with ADJ, forced onto small
+    batches) against the oracle's nw.py:178-199 / 251-267, from the engine's own Q and E."""
+    monkeypatch.setenv("B200DP_V3MIN", "1")
+    if ctas:
+        monkeypatch.setenv("B200DP_CTAS", str(ctas))
+    theta, A = rand_inputs(B, N, M, seed=11)
+    Et = torch.linspace(0.5, 1.5, B)
+    g = torch.Generator().manual_seed(12)
+    Zt = torch.randn(B, N + 2, M + 2, generator=g)
+    ZA = torch.randn(B, N, M, generator=g) * 0.1 if with_za else None
+    Vt_o, Q_o = O.forward_pass(theta.numpy(), A.numpy(), mode)
+    E_o = O.backward_pass(Et.numpy(), Q_o, mode)
+    Vtd_o, Qd_o = O.adjoint_forward_pass(Q_o, Zt.numpy(), ZA.numpy() if with_za else np.zeros((B, N, M), np.float32))
+    Ed_o = O.adjoint_backward_pass(E_o, Q_o, Qd_o)
+    Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), mode)
+    E = ops.backward_pass(Et.to(dev()), Q, mode, N=N)
+    res = ops.adjoint_pair_fast(Q, E, Zt.to(dev()), ZA.to(dev()) if with_za else None)
+    assert res is not None
+    Vtd, Ed = res
+    scale = float(np.abs(Vtd_o).max()) + 1.0
+    np.testing.assert_allclose(Vtd.cpu().numpy(), Vtd_o, rtol=0, atol=2e-5 * scale)
+    np.testing.assert_allclose(Ed.cpu().numpy(), Ed_o, rtol=0, atol=1e-4 * max(1.0, float(np.abs(Ed_o).max())))
+    # and the same answer as the general kernels on the same inputs
+    monkeypatch.setenv("B200DP_V3", "0")
+    assert ops.adjoint_pair_fast(Q, E, Zt.to(dev()), None) is None
+    Vtd2, Qd2 = ops.adjoint_forward_pass(Q, Zt.to(dev()), ZA.to(dev()) if with_za else torch.zeros(B, N, M, device=dev()))
+    Ed2 = ops.adjoint_backward_pass(E, Q, Qd2)
+    np.testing.assert_allclose(Vtd.cpu().numpy(), Vtd2.cpu().numpy(), rtol=0, atol=2e-5 * scale)
+    np.testing.assert_allclose(Ed.cpu().numpy(), Ed2.cpu().numpy(), rtol=0,
+                               atol=1e-4 * max(1.0, float(np.abs(Ed_o).max())))
+
+
+def test_double_backward_large_batch_takes_the_chained_adjoint(ops):
+    """Autograd double backward on a batch the chained kernels take by default."""
+    from deepblast_b200.nw_cuda import NeedlemanWunschDecoder
+    B, N, M = 2 * torch.cuda.get_device_properties(0).multi_processor_count + 3, 64, 96
+    theta_h, A_h = rand_inputs(B, N, M, seed=21)
+    W_h = torch.randn(B, N, M, generator=torch.Generator().manual_seed(22))
+    theta = theta_h.to(dev()).requires_grad_()
+    A = A_h.to(dev()).requires_grad_()
+    dec = NeedlemanWunschDecoder('softmax')
+    aln = dec.decode(theta, A)
+    (aln * W_h.to(dev())).sum().backward()
+    idx = [0, 5, B - 1]
+    Vt_o, Q_o, E_o = O.decode(theta_h[idx].numpy(), A_h[idx].numpy(), "nw")
+    Zt = np.zeros((len(idx), N + 2, M + 2), np.float32)
+    Zt[:, 1:-1, 1:-1] = W_h[idx].numpy()
+    _, Qd_o = O.adjoint_forward_pass(Q_o, Zt, np.zeros((len(idx), N, M), np.float32))
+    Ed_o = O.adjoint_backward_pass(E_o, Q_o, Qd_o)
+    scale = max(1.0, float(np.abs(Ed_o).max()))
+    np.testing.assert_allclose(theta.grad[idx].cpu().numpy(), Ed_o[:, 1:-1, 1:-1], rtol=0, atol=1e-4 * scale)
