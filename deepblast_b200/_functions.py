@@ -17,7 +17,10 @@ from . import ops
 def make_classes(mode, prefix):
     class FunctionBackward(torch.autograd.Function):
         @staticmethod
-        def forward(ctx, theta, A, Et, Q, operator):
+        def forward(ctx, theta, A, Et, Q, operator, interior=False, keep_interior=False):
+            # `interior` (not part of the reference's signature, nw_cuda.py:212): return
+            # E[:, 1:-1, 1:-1] instead of the padded E, so that the double backward receives the
+            # gradient of the interior directly instead of a zero-padded copy it would slice again
             if operator != 'softmax':
                 raise NotImplementedError(
                     "CUDA variant only supports 'softmax' operator")
@@ -26,34 +29,45 @@ def make_classes(mode, prefix):
             # reference-layout [B,N+2,M+2,3] tensor (converted on the fly)
             if Q.dim() == 4:
                 Q = ops.q_from_reference(Q)
-            E = ops.backward_pass(Et, Q, mode, lens[0], lens[1], N=theta.shape[1])
+            # keep_interior (set by Function.backward when a double backward may follow, i.e.
+            # under create_graph): the chained sweep also keeps a contiguous copy of E's
+            # interior for the adjoint forward sweep
+            if keep_interior:
+                E, Ei = ops.backward_pass(Et, Q, mode, lens[0], lens[1], N=theta.shape[1], keep_interior=True)
+            else:
+                E, Ei = ops.backward_pass(Et, Q, mode, lens[0], lens[1], N=theta.shape[1]), None
             # an unused output gradient arrives as None, not as a tensor of zeros to be read
             ctx.set_materialize_grads(False)
-            ctx.save_for_backward(Q, E)
+            ctx.save_for_backward(Q, E, Ei)
             ctx.others = operator
             ctx.lens = lens
-            return E, A
+            ctx.interior = bool(interior)
+            return (E[:, 1:-1, 1:-1] if interior else E), A
 
         @staticmethod
         def backward(ctx, Ztheta, ZA):
-            Q, E = ctx.saved_tensors
-            if Ztheta is None:
-                Ztheta = torch.zeros_like(E)
-            B, ZN, ZM = Ztheta.shape
+            Q, E, Ei = ctx.saved_tensors
             xl, yl = ctx.lens
-            if xl is None and yl is None and Ztheta.dtype == torch.float32:
+            if xl is None and yl is None and (Ztheta is None or Ztheta.dtype == torch.float32):
                 # large batches of equal-size lattices: both sweeps on the chained kernels
                 # (ZA stays None when the caller did not use the A passthrough: no zeros to read)
-                fast = ops.adjoint_pair_fast(Q, E, Ztheta, ZA)
+                fast = ops.adjoint_pair_fast(Q, E, Ztheta, ZA, interior=ctx.interior, Ei=Ei)
                 if fast is not None:
                     Vtd, Ed = fast
-                    return Ed[:, 1:-1, 1:-1], None, Vtd, None, None, None
+                    return Ed[:, 1:-1, 1:-1], None, Vtd, None, None, None, None, None
+            if Ztheta is None:
+                Ztheta = torch.zeros_like(E)
+            elif ctx.interior:
+                Zpad = torch.zeros_like(E)
+                Zpad[:, 1:-1, 1:-1] = Ztheta
+                Ztheta = Zpad
+            B, ZN, ZM = Ztheta.shape
             if ZA is None:
                 ZA = torch.zeros((B, ZN - 2, ZM - 2), dtype=Ztheta.dtype, device=Ztheta.device)
             Vtd, Qd = ops.adjoint_forward_pass(Q, Ztheta, ZA, xl, yl)
             Ed = ops.adjoint_backward_pass(E, Q, Qd, xl, yl)
             Ed = Ed[:, 1:-1, 1:-1]
-            return Ed, None, Vtd, None, None, None
+            return Ed, None, Vtd, None, None, None, None, None
 
     class Function(torch.autograd.Function):
         @staticmethod
@@ -77,8 +91,8 @@ def make_classes(mode, prefix):
             operator = ctx.others
             if ctx.lens != (None, None):
                 Q._b200dp_lens = ctx.lens
-            E, A = FunctionBackward.apply(theta, A, Et, Q, operator)
-            return E[:, 1:-1, 1:-1], A, None, None, None
+            E, A = FunctionBackward.apply(theta, A, Et, Q, operator, True, torch.is_grad_enabled())
+            return E, A, None, None, None
 
     class Decoder(nn.Module):
         def __init__(self, operator):

@@ -19,6 +19,7 @@ EXPORTS = {
                                        ctypes.POINTER(_ll), ctypes.POINTER(_ll)]),
     "b200dp_fwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "b200dp_bwd": (ctypes.c_int, [_f, _ll, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
+    "b200dp_bwd_keep_interior": (ctypes.c_int, [_f, _ll, _f, _f, _f, ctypes.POINTER(_i), _i, _i, _i, _i, _i, _f]),
     "b200dp_adj_fwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f]),
     "b200dp_adj_bwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f]),
     "b200dp_decode_host_workspace": (ctypes.c_size_t, [_i, _i, _i]),

@@ -502,8 +502,22 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
     return 0;
 }
 
+static int bwd_impl(const float* Et, long long et_stride, const float* Q, float* E, float* Ei, int* wrote_ei,
+                    const int32_t* xlen, const int32_t* ylen, int B, int N, int M, int mode, int flags, void* stream);
+
 int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E, const int32_t* xlen,
                const int32_t* ylen, int B, int N, int M, int mode, int flags, void* stream) {
+    return bwd_impl(Et, et_stride, Q, E, nullptr, nullptr, xlen, ylen, B, N, M, mode, flags, stream);
+}
+
+int b200dp_bwd_keep_interior(const float* Et, long long et_stride, const float* Q, float* E, float* Ei,
+                             int* wrote_ei, int B, int N, int M, int mode, int flags, void* stream) {
+    return bwd_impl(Et, et_stride, Q, E, Ei, wrote_ei, nullptr, nullptr, B, N, M, mode, flags, stream);
+}
+
+static int bwd_impl(const float* Et, long long et_stride, const float* Q, float* E, float* Ei, int* wrote_ei,
+                    const int32_t* xlen, const int32_t* ylen, int B, int N, int M, int mode, int flags, void* stream) {
+    if (wrote_ei) *wrote_ei = 0;
     if (int rc = check_common("b200dp_bwd", B, N, M)) return rc;
     if (mode != B200DP_MODE_NW && mode != B200DP_MODE_SW) return fail(-1, "b200dp_bwd: bad mode");
     if (B == 0) return 0;
@@ -515,6 +529,7 @@ int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E, c
     p.Q = Q;
     p.QdE = nullptr;
     p.E = E;
+    p.Ei = Ei;
     p.d = PairDims{xlen, ylen, B, N, M};
     p.ql = q_layout(N, M);
     p.i0 = mode == B200DP_MODE_SW ? 2 : 1;
@@ -526,6 +541,7 @@ int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E, c
         !getenv("B200DP_WARPS")) {
         // large batches of equal-size lattices: chained single-warp kernel (softdp_bwd3.cuh)
         int rc3 = launch_bwd3(p, B, N, M, mode, flags, st);
+        if (rc3 == 0 && wrote_ei && Ei) *wrote_ei = 1;      // only the chained kernel writes the second copy
         if (rc3 <= 0) return rc3 < 0 ? -rc3 - 1000 : 0;
     }
     if (tma && !(flags & B200DP_V1_KERNELS) && !env_v1() && M >= 2 * kG) {
@@ -714,6 +730,7 @@ int b200dp_adj_bwd3(const float* Q, const float* QdE, float* Ed, int B, int N, i
     p.Q = Q;
     p.QdE = QdE;
     p.E = Ed;
+    p.Ei = nullptr;
     p.d = PairDims{nullptr, nullptr, B, N, M};
     p.ql = q_layout(N, M);
     p.i0 = 1;

@@ -22,6 +22,8 @@ struct BwdParams {
     const float* Q;       // strip-major storage base
     const float* QdE;     // adjoint backward only (softdp_bwd3_kernel<.., ADJ>): strip-major Qd * E
     float* E;             // [B, N+2, M+2] row-major (adjoint backward: Ed)
+    float* Ei;            // optional second copy of the interior, contiguous [B, N, M] (softdp_bwd3 only):
+                          // what the adjoint forward sweep reads through TMA if a double backward follows
     PairDims d;
     QLayout ql;
     int i0;

@@ -54,7 +54,8 @@ __host__ __device__ inline size_t bwd3_smem_bytes(int M) {
 // FULL = all 32 rows of the strip are inside the lattice (no store predicates).
 template <bool FULL>
 __device__ __forceinline__ void bwd3_drain_tile(const float* __restrict__ stage, float* __restrict__ Erow0, int tc,
-                                                int M, int rmax, int pitch, int t, int segrow) {
+                                                int M, int rmax, int pitch, int t, int segrow,
+                                                float* __restrict__ Ei_row0 = nullptr) {
     int sr0 = (segrow + M + 30 - tc * kTile) % kB2StageSteps - t;
     sr0 += (sr0 < 0) ? kB2StageSteps : 0;
     const float* p0 = stage + sr0 * kB2StagePitch;
@@ -72,6 +73,13 @@ __device__ __forceinline__ void bwd3_drain_tile(const float* __restrict__ stage,
 #pragma unroll
         for (int q = 0; q < 8; ++q)
             if (FULL || r0 + q < rmax) dstp[(r0 + q) * pitch] = v[q];
+        if (Ei_row0) {
+            // the same rows into the contiguous interior copy (pitch M, 128-byte aligned lines)
+            float* d2 = Ei_row0 + tc * kTile + t;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (FULL || r0 + q < rmax) d2[(r0 + q) * M] = v[q];
+        }
     }
 }
 
@@ -164,8 +172,9 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
             float* Eb = p.E + (long long)pair * Epair;
             float* Er = Eb + (long long)(kb * kTile + 1) * (M + 2);
             const int rmax = N - kb * kTile;
-            if (rmax >= kTile) bwd3_drain_tile<true>(stage, Er, d_tc, M, kTile, M + 2, t, d_segrow);
-            else bwd3_drain_tile<false>(stage, Er, d_tc, M, rmax, M + 2, t, d_segrow);
+            float* Eir = (!ADJ && p.Ei) ? p.Ei + ((long long)pair * N + kb * kTile) * M : nullptr;
+            if (rmax >= kTile) bwd3_drain_tile<true>(stage, Er, d_tc, M, kTile, M + 2, t, d_segrow, Eir);
+            else bwd3_drain_tile<false>(stage, Er, d_tc, M, rmax, M + 2, t, d_segrow, Eir);
             drained++;
             if (--d_tc < 0) {
                 // strip complete: zero borders, E[N+1, M+1] = Et  (nw.py:125-127, 347)

@@ -9,6 +9,8 @@ from the reference's dense padded [B, N+2, M+2, 3].  Only the x and y states of 
 are stored; the m state is implied (Q sums to 1 over the states, Qd to 0), and q_x = -1
 marks a cell whose Q is identically zero (first row / column of the sw.py lattice).
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -138,14 +140,29 @@ def forward_pass(theta, A, mode="nw", xlen=None, ylen=None, flags=0):
     return Vt, Q
 
 
-def backward_pass(Et, Q, mode="nw", xlen=None, ylen=None, flags=0, N=None):
+def backward_pass(Et, Q, mode="nw", xlen=None, ylen=None, flags=0, N=None, keep_interior=False):
     """Et [B] (any stride), Q (strip-major view + N, or dense reference layout)
-    -> E [B,N+2,M+2].  nw.py:138-175, 347-352."""
+    -> E [B,N+2,M+2].  nw.py:138-175, 347-352.  keep_interior=True returns (E, Ei) with Ei a
+    contiguous copy of E[:, 1:-1, 1:-1] written by the sweep itself where the chained kernel
+    takes the batch (None otherwise): the operand the chained adjoint forward sweep reads."""
     Q, N, M = _as_engine_q(Q, N)
     B = Q.shape[0]
     _check_in("Et", Et, (B,))
     Et = Et.detach()
     xlen, ylen = _lens(xlen, ylen, B, N, M, Q.device)
+    if keep_interior and xlen is None and B > 0:
+        with torch.cuda.device(Q.device):
+            E = torch.empty((B, N + 2, M + 2), dtype=torch.float32, device=Q.device)
+            Ei = None
+            wrote = _lib._i(0)
+            if _lib.lib().b200dp_adj3_applicable(B, N, M):
+                Ei = torch.empty((B, N, M), dtype=torch.float32, device=Q.device)
+            rc = _lib.lib().b200dp_bwd_keep_interior(_ptr(Et), Et.stride(0), _ptr(Q), _ptr(E), _ptr(Ei),
+                                                     ctypes.byref(wrote), B, N, M, MODES[mode], flags, _stream(Q))
+            _lib.check(rc, "b200dp_bwd_keep_interior")
+        return E, (Ei if wrote.value else None)
+    if keep_interior:
+        return backward_pass(Et, Q, mode, xlen, ylen, flags, N), None
     with torch.cuda.device(Q.device):
         alloc = torch.zeros if xlen is not None else torch.empty
         E = alloc((B, N + 2, M + 2), dtype=torch.float32, device=Q.device)
@@ -192,24 +209,31 @@ def adjoint_backward_pass(E, Q, Qd, xlen=None, ylen=None, flags=0):
     return Ed
 
 
-def adjoint_pair_fast(Q, E, Ztheta, ZA=None, N=None, flags=0):
+def adjoint_pair_fast(Q, E, Ztheta, ZA=None, N=None, flags=0, interior=False, Ei=None):
     """Both adjoint sweeps on the chained kernels (large batches of equal-size lattices):
-    Q (strip-major), E, Ztheta [B,N+2,M+2], ZA [B,N,M] or None (= zeros) -> (Vtd [B],
-    Ed [B,N+2,M+2]), or None when the shape is not taken (use adjoint_forward_pass /
-    adjoint_backward_pass).  The forward sweep multiplies Qd by E on the fly (it reads the
-    interiors of Ztheta and E as contiguous [B,N,M] copies through TMA), so the backward
-    sweep needs Q and that product only."""
-    B, N2, M2 = Ztheta.shape
+    Q (strip-major), E [B,N+2,M+2], Ztheta [B,N+2,M+2] (or, with interior=True, its interior
+    [B,N,M]; None = zeros), ZA [B,N,M] or None (= zeros) -> (Vtd [B], Ed [B,N+2,M+2]), or
+    None when the shape is not taken (use adjoint_forward_pass / adjoint_backward_pass).
+    The forward sweep multiplies Qd by E on the fly (it reads the interiors of Ztheta and E
+    as contiguous [B,N,M] tensors through TMA), so the backward sweep needs Q and that
+    product only."""
+    B, N2, M2 = E.shape
     N, M = N2 - 2, M2 - 2
     if Q.dim() != 5 or not _is_engine_q(Q, N, M) or not Q.is_cuda:
         return None
     with torch.cuda.device(Q.device):
         if not _lib.lib().b200dp_adj3_applicable(B, N, M):
             return None
-        _check_in("Ztheta", Ztheta, (B, N2, M2))
         _check_in("E", E, (B, N2, M2))
-        zt = Ztheta.detach()[:, 1:-1, 1:-1].contiguous()
-        e = E.detach()[:, 1:-1, 1:-1].contiguous()
+        if Ztheta is None:
+            zt = torch.zeros((B, N, M), dtype=torch.float32, device=Q.device)
+        elif interior:
+            _check_in("Ztheta", Ztheta, (B, N, M))
+            zt = Ztheta.detach().contiguous()
+        else:
+            _check_in("Ztheta", Ztheta, (B, N2, M2))
+            zt = Ztheta.detach()[:, 1:-1, 1:-1].contiguous()
+        e = Ei if Ei is not None else E.detach()[:, 1:-1, 1:-1].contiguous()
         za = None
         if ZA is not None:
             _check_in("ZA", ZA, (B, N, M))

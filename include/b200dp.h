@@ -81,6 +81,13 @@ int b200dp_bwd(const float* Et, long long et_stride, const float* Q, float* E,
                const int32_t* xlen, const int32_t* ylen, int B, int N, int M,
                int mode, int flags, void* stream);
 
+/* b200dp_bwd that, where the chained kernel takes the batch, also writes the interior of E as
+ * a contiguous [B, N, M] tensor Ei (what b200dp_adj_fwd3 reads if a double backward follows);
+ * *wrote_ei = 1 if it did, 0 if Ei was left untouched (the caller then slices E itself). */
+int b200dp_bwd_keep_interior(const float* Et, long long et_stride, const float* Q, float* E,
+                             float* Ei, int* wrote_ei, int B, int N, int M, int mode, int flags,
+                             void* stream);
+
 /* replaces _adjoint_forward_pass_kernel, deepblast/nw_cuda.py:105-139:
  * Q, Ztheta (padded), ZA -> Vtd, Qd. */
 int b200dp_adj_fwd(const float* Q, const float* Ztheta, const float* ZA, float* Vtd,

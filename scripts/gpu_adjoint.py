@@ -47,5 +47,19 @@ for B, N, M in ((1024, 256, 256), (1024, 512, 512), (64, 256, 256)):
           "chained adjoint pair (incl. the two interior copies) %.3f ms | training step (4 sweeps) %.1f -> %.1f Gcell/s" % (
               B, N, M, f, b, af, cells * 32 / af / 1e6, ab, cells * 32 / ab / 1e6, fp,
               cells / (f + b + af + ab) / 1e6, cells / (f + b + (fp if fp == fp else af + ab)) / 1e6), flush=True)
+    if fast is not None:
+        from deepblast_b200 import _lib
+        L = _lib.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        zt = Zt[:, 1:-1, 1:-1].contiguous()
+        e = E[:, 1:-1, 1:-1].contiguous()
+        QdE = ops.q_empty(B, N, M, dev)
+        Vtd2 = torch.empty(B, device=dev)
+        Ed = torch.empty(B, N + 2, M + 2, device=dev)
+        tc = timeit(lambda: (Zt[:, 1:-1, 1:-1].contiguous(), E[:, 1:-1, 1:-1].contiguous()))
+        tf = timeit(lambda: L.b200dp_adj_fwd3(Q.data_ptr(), zt.data_ptr(), None, e.data_ptr(), Vtd2.data_ptr(),
+                                              QdE.data_ptr(), B, N, M, 0, st))
+        tb = timeit(lambda: L.b200dp_adj_bwd3(Q.data_ptr(), QdE.data_ptr(), Ed.data_ptr(), B, N, M, 0, st))
+        print("    pieces: interior copies %.3f  adj_fwd3 %.3f  adj_bwd3 %.3f ms" % (tc, tf, tb), flush=True)
     del fast
     del theta, A, Q, Qd, E, Zt, ZA
