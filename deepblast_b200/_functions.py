@@ -51,10 +51,10 @@ def make_classes(mode, prefix):
             if xl is None and yl is None and (Ztheta is None or Ztheta.dtype == torch.float32):
                 # large batches of equal-size lattices: both sweeps on the chained kernels
                 # (ZA stays None when the caller did not use the A passthrough: no zeros to read)
-                fast = ops.adjoint_pair_fast(Q, E, Ztheta, ZA, interior=ctx.interior, Ei=Ei)
+                fast = ops.adjoint_pair_fast(Q, E, Ztheta, ZA, interior=ctx.interior, Ei=Ei, interior_out=True)
                 if fast is not None:
-                    Vtd, Ed = fast
-                    return Ed[:, 1:-1, 1:-1], None, Vtd, None, None, None, None, None
+                    Vtd, Ed = fast                      # Ed: contiguous [B, N, M], nothing to slice or clone
+                    return Ed, None, Vtd, None, None, None, None, None
             if Ztheta is None:
                 Ztheta = torch.zeros_like(E)
             elif ctx.interior:

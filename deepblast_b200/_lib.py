@@ -26,7 +26,7 @@ EXPORTS = {
     "b200dp_decode_host": (ctypes.c_int, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f, ctypes.c_size_t, _i, _f]),
     "b200dp_adj3_applicable": (ctypes.c_int, [_i, _i, _i]),
     "b200dp_adj_fwd3": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f]),
-    "b200dp_adj_bwd3": (ctypes.c_int, [_f, _f, _f, _i, _i, _i, _i, _f]),
+    "b200dp_adj_bwd3": (ctypes.c_int, [_f, _f, _f, _f, _i, _i, _i, _i, _f]),
     "b200dp_mxent_fwd": (ctypes.c_int, [_f, _f, _ll, _ll, _f, _f, _f, _i, _i, _i, _f, _f, _f]),
     "b200dp_mxent_bwd": (ctypes.c_int, [_f, _f, _ll, _ll, _f, _f, _f, _i, _i, _i, _f, _f, _f, _f]),
     "b200dp_traceback": (ctypes.c_int, [_f, _ll, _ll, _ll, _f, _f, _i, _i, _i, _i, _f, _i, _f, _f]),

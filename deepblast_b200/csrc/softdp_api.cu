@@ -707,21 +707,31 @@ int b200dp_adj_fwd3(const float* Q, const float* Zt, const float* ZA, const floa
     p.has_e = E ? 1 : 0;
     p.pf_tiles = 0;
     p.pf_dist = 0;
-    const size_t smem = fwd3_smem_bytes<1, 3, true>(M);
-    int grid = 0;
-    if (chained_grid(B, smem, grid) < 0) return fail(-3, "b200dp_adj_fwd3: M too large for shared memory");
-    auto kern = softdp_fwd3_kernel<false, 1, 3, 0, true>;
-    if (int rc = set_smem(kern, smem, "b200dp_adj_fwd3")) return rc;
-    kern<<<grid, 32, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmZ, tmA, tmE, tmE, p);
+    // three Q tile slots unless two save a whole round of CTAs (M >= 512 at 1024 pairs)
+    int g3 = 0, g2 = 0;
+    const size_t s3 = fwd3_smem_bytes<1, 3, true, 3>(M), s2 = fwd3_smem_bytes<1, 3, true, 2>(M);
+    const int r3 = chained_grid(B, s3, g3), r2 = chained_grid(B, s2, g2);
+    if (r2 < 0) return fail(-3, "b200dp_adj_fwd3: M too large for shared memory");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (r3 > 0 && r3 <= r2) {
+        auto kern = softdp_fwd3_kernel<false, 1, 3, 0, true, 3>;
+        if (int rc = set_smem(kern, s3, "b200dp_adj_fwd3")) return rc;
+        kern<<<g3, 32, s3, st>>>(tmZ, tmA, tmE, tmE, p);
+    } else {
+        auto kern = softdp_fwd3_kernel<false, 1, 3, 0, true, 2>;
+        if (int rc = set_smem(kern, s2, "b200dp_adj_fwd3")) return rc;
+        kern<<<g2, 32, s2, st>>>(tmZ, tmA, tmE, tmE, p);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "b200dp_adj_fwd3 launch");
     return 0;
 }
 
-int b200dp_adj_bwd3(const float* Q, const float* QdE, float* Ed, int B, int N, int M, int flags, void* stream) {
+int b200dp_adj_bwd3(const float* Q, const float* QdE, float* Ed, float* Ed_interior, int B, int N, int M, int flags,
+                    void* stream) {
     if (int rc = check_common("b200dp_adj_bwd3", B, N, M)) return rc;
     if (B == 0) return 0;
-    if (!Q || !QdE || !Ed) return fail(-1, "b200dp_adj_bwd3: null pointer");
+    if (!Q || !QdE || (!Ed && !Ed_interior)) return fail(-1, "b200dp_adj_bwd3: null pointer");
     if (!adj3_shape_ok(B, N, M)) return fail(-4, "b200dp_adj_bwd3: shape not taken by the chained kernels (b200dp_adj3_applicable)");
     if (!aligned(Q, 16) || !aligned(QdE, 16)) return fail(-1, "b200dp_adj_bwd3: Q / QdE storage must be 16-byte aligned");
     BwdParams p;
@@ -730,7 +740,7 @@ int b200dp_adj_bwd3(const float* Q, const float* QdE, float* Ed, int B, int N, i
     p.Q = Q;
     p.QdE = QdE;
     p.E = Ed;
-    p.Ei = nullptr;
+    p.Ei = Ed_interior;
     p.d = PairDims{nullptr, nullptr, B, N, M};
     p.ql = q_layout(N, M);
     p.i0 = 1;

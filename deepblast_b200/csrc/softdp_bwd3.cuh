@@ -70,9 +70,11 @@ __device__ __forceinline__ void bwd3_drain_tile(const float* __restrict__ stage,
             const float* ps = (r > sr0) ? p1 : p0;
             v[q] = ps[-(kB2StagePitch - 1) * r];
         }
+        if (Erow0) {                                  // (ADJ may ask for the interior only)
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-            if (FULL || r0 + q < rmax) dstp[(r0 + q) * pitch] = v[q];
+            for (int q = 0; q < 8; ++q)
+                if (FULL || r0 + q < rmax) dstp[(r0 + q) * pitch] = v[q];
+        }
         if (Ei_row0) {
             // the same rows into the contiguous interior copy (pitch M, 128-byte aligned lines)
             float* d2 = Ei_row0 + tc * kTile + t;
@@ -172,20 +174,22 @@ __global__ void __launch_bounds__(32) softdp_bwd3_kernel(BwdParams p) {
             float* Eb = p.E + (long long)pair * Epair;
             float* Er = Eb + (long long)(kb * kTile + 1) * (M + 2);
             const int rmax = N - kb * kTile;
-            float* Eir = (!ADJ && p.Ei) ? p.Ei + ((long long)pair * N + kb * kTile) * M : nullptr;
+            if (ADJ && !p.E) Er = nullptr;
+            float* Eir = p.Ei ? p.Ei + ((long long)pair * N + kb * kTile) * M : nullptr;
             if (rmax >= kTile) bwd3_drain_tile<true>(stage, Er, d_tc, M, kTile, M + 2, t, d_segrow, Eir);
             else bwd3_drain_tile<false>(stage, Er, d_tc, M, rmax, M + 2, t, d_segrow, Eir);
             drained++;
             if (--d_tc < 0) {
                 // strip complete: zero borders, E[N+1, M+1] = Et  (nw.py:125-127, 347)
                 const int i = kb * kTile + t + 1;
-                if (i <= N) {
+                const bool padded = !ADJ || p.E != nullptr;
+                if (padded && i <= N) {
                     Eb[(long long)i * (M + 2)] = 0.f;
                     Eb[(long long)i * (M + 2) + M + 1] = 0.f;
                 }
-                if (kb == 0)
+                if (padded && kb == 0)
                     for (int col = t; col < M + 2; col += 32) Eb[col] = 0.f;
-                if (d_k == 0) {
+                if (padded && d_k == 0) {
                     const float et = ADJ ? 0.f : p.Et[(long long)pair * p.et_stride];
                     for (int col = t; col < M + 2; col += 32)
                         Eb[(long long)(N + 1) * (M + 2) + col] = (col == M + 1) ? et : 0.f;

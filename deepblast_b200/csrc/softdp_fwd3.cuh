@@ -47,9 +47,7 @@ namespace b200dp {
 // holds Qd * E (what the adjoint backward sweep consumes), or Qd when E is absent.  A cell
 // whose Q carries the zero mark has Vd = ztheta (its diagonal predecessor is on the zero
 // border) and Qd = 0.  Vtd = Vd[N, M] = sum_j hd[N, j].
-constexpr int kAdj3QRing = 3;
-
-template <int NCH, int RING, bool ADJ = false>
+template <int NCH, int RING, bool ADJ = false, int kAdj3QRing = 3>
 __host__ __device__ inline size_t fwd3_smem_bytes(int M) {
     size_t b = (size_t)RING * NCH * (ADJ ? 6144 : 4096);   // [RING][2 NCH groups][theta, A (, E)][16][16] fp32
     if (ADJ) b += (size_t)kAdj3QRing * kDiagElems * 4 + (size_t)kAdj3QRing * 8;
@@ -88,7 +86,7 @@ __device__ __forceinline__ float adj3_step(float zt, float za, float e, float qx
     return hn;
 }
 
-template <bool SWM, int NCH, int RING, int DBG = 0, bool ADJ = false>
+template <bool SWM, int NCH, int RING, int DBG = 0, bool ADJ = false, int kAdj3QRing = 3>
 __global__ void __launch_bounds__(32) softdp_fwd3_kernel(const __grid_constant__ CUtensorMap tm_theta,
                                                          const __grid_constant__ CUtensorMap tm_A,
                                                          const __grid_constant__ CUtensorMap tm_pf_theta,

@@ -209,7 +209,7 @@ def adjoint_backward_pass(E, Q, Qd, xlen=None, ylen=None, flags=0):
     return Ed
 
 
-def adjoint_pair_fast(Q, E, Ztheta, ZA=None, N=None, flags=0, interior=False, Ei=None):
+def adjoint_pair_fast(Q, E, Ztheta, ZA=None, N=None, flags=0, interior=False, Ei=None, interior_out=False):
     """Both adjoint sweeps on the chained kernels (large batches of equal-size lattices):
     Q (strip-major), E [B,N+2,M+2], Ztheta [B,N+2,M+2] (or, with interior=True, its interior
     [B,N,M]; None = zeros), ZA [B,N,M] or None (= zeros) -> (Vtd [B], Ed [B,N+2,M+2]), or
@@ -243,10 +243,12 @@ def adjoint_pair_fast(Q, E, Ztheta, ZA=None, N=None, flags=0, interior=False, Ei
         rc = _lib.lib().b200dp_adj_fwd3(_ptr(Q), _ptr(zt), _ptr(za), _ptr(e), _ptr(Vtd), _ptr(QdE),
                                         B, N, M, flags, _stream(Q))
         _lib.check(rc, "b200dp_adj_fwd3")
-        Ed = torch.empty((B, N2, M2), dtype=torch.float32, device=Q.device)
-        rc = _lib.lib().b200dp_adj_bwd3(_ptr(Q), _ptr(QdE), _ptr(Ed), B, N, M, flags, _stream(Q))
+        # interior_out: Ed[:, 1:-1, 1:-1] as a contiguous [B, N, M] tensor, no padded Ed at all
+        Ed = None if interior_out else torch.empty((B, N2, M2), dtype=torch.float32, device=Q.device)
+        Edi = torch.empty((B, N, M), dtype=torch.float32, device=Q.device) if interior_out else None
+        rc = _lib.lib().b200dp_adj_bwd3(_ptr(Q), _ptr(QdE), _ptr(Ed), _ptr(Edi), B, N, M, flags, _stream(Q))
         _lib.check(rc, "b200dp_adj_bwd3")
-    return Vtd, Ed
+    return Vtd, (Edi if interior_out else Ed)
 
 
 def traceback_batch(grad, xlen=None, ylen=None, variant="cuda"):

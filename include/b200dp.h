@@ -106,12 +106,13 @@ int b200dp_adj_bwd(const float* E, const float* Q, const float* Qd, float* Ed,
  *   b200dp_adj_fwd3: Q, Zt = the INTERIOR of Ztheta as a contiguous [B, N, M] tensor, ZA
  *     [B, N, M] or NULL (= zeros, the usual case), E interior [B, N, M] or NULL
  *     -> Vtd [B] and the strip-major stream QdE = Qd * E (Qd itself when E is NULL);
- *   b200dp_adj_bwd3: Q, QdE -> Ed [B, N+2, M+2] (zero borders). */
+ *   b200dp_adj_bwd3: Q, QdE -> Ed [B, N+2, M+2] (zero borders) and / or its interior as a
+ *     contiguous [B, N, M] tensor (either pointer may be NULL, not both). */
 int b200dp_adj3_applicable(int B, int N, int M);
 int b200dp_adj_fwd3(const float* Q, const float* Zt, const float* ZA, const float* E, float* Vtd,
                     float* QdE, int B, int N, int M, int flags, void* stream);
-int b200dp_adj_bwd3(const float* Q, const float* QdE, float* Ed, int B, int N, int M, int flags,
-                    void* stream);
+int b200dp_adj_bwd3(const float* Q, const float* QdE, float* Ed, float* Ed_interior, int B, int N,
+                    int M, int flags, void* stream);
 
 /* replaces the Python walk NeedlemanWunschDecoder.traceback,
  * deepblast/nw.py:401-444 (variant 0) / deepblast/nw_cuda.py:273-317 (variant 1),

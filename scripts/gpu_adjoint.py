@@ -59,7 +59,7 @@ for B, N, M in ((1024, 256, 256), (1024, 512, 512), (64, 256, 256)):
         tc = timeit(lambda: (Zt[:, 1:-1, 1:-1].contiguous(), E[:, 1:-1, 1:-1].contiguous()))
         tf = timeit(lambda: L.b200dp_adj_fwd3(Q.data_ptr(), zt.data_ptr(), None, e.data_ptr(), Vtd2.data_ptr(),
                                               QdE.data_ptr(), B, N, M, 0, st))
-        tb = timeit(lambda: L.b200dp_adj_bwd3(Q.data_ptr(), QdE.data_ptr(), Ed.data_ptr(), B, N, M, 0, st))
+        tb = timeit(lambda: L.b200dp_adj_bwd3(Q.data_ptr(), QdE.data_ptr(), Ed.data_ptr(), None, B, N, M, 0, st))
         print("    pieces: interior copies %.3f  adj_fwd3 %.3f  adj_bwd3 %.3f ms" % (tc, tf, tb), flush=True)
     del fast
     del theta, A, Q, Qd, E, Zt, ZA
