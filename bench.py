@@ -53,7 +53,7 @@ def kernel_name(dom, B, N, M, varlen):
     kernels otherwise."""
     import torch
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    chained = (not varlen) and B >= 2 * sms and N >= 32 and M >= 64 and M % (16 if dom == "fwd" else 32) == 0
+    chained = (not varlen) and B >= 4 * sms and N >= 32 and M >= 64 and M % (16 if dom == "fwd" else 32) == 0
     return f"softdp_{dom}{3 if chained else 2}_kernel"
 
 

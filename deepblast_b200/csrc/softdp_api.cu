@@ -79,6 +79,12 @@ bool dev_info(DevInfo& out) {
     return true;
 }
 
+// The chained kernels run one warp per pair: their time is one pair's latency, flat up to ~7
+// pairs per SM, while the hand-off kernels (W warps per pair) scale with the batch.  Measured
+// on B200 the two meet at about 4 pairs per SM (256 x 256: forward 0.177 ms chained against
+// 0.085 ms hand-off at 2 pairs per SM).
+constexpr int kChainedMinPairsPerSM = 4;
+
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // rank-3 map over a contiguous [B, N, M] fp32 tensor, box 32 cols x 32 rows x 1
@@ -241,7 +247,7 @@ int launch_bwd3(const BwdParams& p, int B, int N, int M, int mode, int flags, cu
     if (const char* e = getenv("B200DP_V3")) if (atoi(e) == 0) return 1;
     DevInfo di;
     if (!dev_info(di)) return 1;
-    int minB = 2 * di.sms;
+    int minB = kChainedMinPairsPerSM * di.sms;
     if (const char* e = getenv("B200DP_V3MIN")) minB = atoi(e);
     if (B < minB || N < kTile || M < 64 || M % 32 != 0) return 1;
     int want_ring = 0;
@@ -307,7 +313,7 @@ int launch_fwd3(const CUtensorMap& tmT, const CUtensorMap& tmA, FwdParams p, int
     if (const char* e = getenv("B200DP_V3")) if (atoi(e) == 0) return 1;
     DevInfo di;
     if (!dev_info(di)) return 1;
-    int minB = 2 * di.sms;
+    int minB = kChainedMinPairsPerSM * di.sms;
     if (const char* e = getenv("B200DP_V3MIN")) minB = atoi(e);
     if (B < minB || N < kTile) return 1;
     const int K = (N + kTile - 1) / kTile;
@@ -660,7 +666,7 @@ static bool adj3_shape_ok(int B, int N, int M) {
     if (const char* e = getenv("B200DP_V3")) if (atoi(e) == 0) return false;
     DevInfo di;
     if (!dev_info(di)) return false;
-    int minB = 2 * di.sms;
+    int minB = 1;      // measured on B200: the chained adjoint pair beats the general kernels at every batch size
     if (const char* e = getenv("B200DP_V3MIN")) minB = atoi(e);
     return B >= minB && N >= kTile && M >= 64 && M % 32 == 0 && get_encode() != nullptr;
 }

@@ -394,8 +394,8 @@ def test_ragged_many_pairs_per_cta_handoff(ops, kern):
 
 def test_c4_shape_on_the_chained_kernels(ops):
     """BASELINE configs[3] per-GPU lattice (512 x 512) at the smallest batch the chained
-    kernels take by default (2 pairs per SM): oracle on a sample, size-independent properties on all."""
-    B, N, M = 2 * torch.cuda.get_device_properties(0).multi_processor_count + 4, 512, 512
+    kernels take by default (4 pairs per SM): oracle on a sample, size-independent properties on all."""
+    B, N, M = 4 * torch.cuda.get_device_properties(0).multi_processor_count + 4, 512, 512
     g = torch.Generator(device=dev()).manual_seed(4)
     th = torch.rand(B, N, M, generator=g, device=dev())
     a = -torch.rand(B, N, M, generator=g, device=dev())
