@@ -409,6 +409,11 @@ def main():
             "roofline": {"bound": "hbm", "kernel": kernel_name(dom, Bg, N, M, xlen is not None), "achieved": ach,
                          "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                         # measured DRAM bytes of that launch (ncu, profiles/traffic.json) over the live
+                         # duration: the kernels store two of the three Q states, so they move fewer bytes
+                         # than the 36 B/cell contract `achieved` is quoted on
+                         "traffic_GBps": (traffic / ((fwd_ms if dom == "fwd" else bwd_ms) * 1e-3) / 1e9) if traffic else None,
+                         "traffic_frac": (traffic / ((fwd_ms if dom == "fwd" else bwd_ms) * 1e-3) / 1e9 / peak) if traffic else None,
                          "algorithmic_bytes_per_cell": BYTES_FWD if dom == "fwd" else BYTES_BWD,
                          "fwd": {"ms": fwd_ms, "GBps": fwd_gbs, "frac": fwd_gbs / peak},
                          "bwd": {"ms": bwd_ms, "GBps": bwd_gbs, "frac": bwd_gbs / peak},
