@@ -187,8 +187,10 @@ def reference_arm(args):
         xlen, ylen = zipf_lengths(Bg, np.random.default_rng(0))
     vals, times = [], []
     cores, sample = 1, ""
+    # every step is a bounded sample of the workload; the whole run stays within a few minutes
+    per_step_s = min(args.cpu_seconds, max(2.0, 150.0 / max(1, args.warmup + args.steps)))
     for it in range(args.warmup + args.steps):
-        v, cores, sample, dt = cpu_port_throughput(mode, N, M, xlen, ylen, target_s=args.cpu_seconds, seed=2 + it)
+        v, cores, sample, dt = cpu_port_throughput(mode, N, M, xlen, ylen, target_s=per_step_s, seed=2 + it)
         if it >= args.warmup:
             vals.append(v); times.append(dt)
     value = float(np.mean(vals))
