@@ -146,7 +146,7 @@ def cpu_port_throughput(mode, N, M, xlen=None, ylen=None, target_s=12.0, seed=2)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     rng = np.random.default_rng(seed)
 
-    def run(Bs):
+    def make(Bs):
         theta = rng.random((Bs, N, M), dtype=np.float32)
         A = -rng.random((Bs, N, M), dtype=np.float32)
         xl = None if xlen is None else np.resize(xlen, Bs).astype(np.int32)
@@ -154,23 +154,29 @@ def cpu_port_throughput(mode, N, M, xlen=None, ylen=None, target_s=12.0, seed=2)
         cells = Bs * N * M if xl is None else int((xl.astype(np.int64) * yl).sum())
         if mode == "sw" and xl is None:
             cells = Bs * (N - 1) * (M - 1)
+        return theta, A, xl, yl, cells
+
+    def run(batch):
+        theta, A, xl, yl, cells = batch
         t0 = time.perf_counter()
         O.fwd_bwd_batch_f32(theta, A, mode, xl, yl, nthreads=cores, want_E=True)
         return cells, time.perf_counter() - t0
 
-    run(max(cores, 8))                                   # warm the .so and the thread pool
-    cells, dt = run(4 * max(cores, 8))                   # calibration
+    run(make(max(cores, 8)))                             # warm the .so and the thread pool
+    cells, dt = run(make(4 * max(cores, 8)))             # calibration
     rate = cells / dt
     per_pair = (N * M) if xlen is None else float(np.mean(np.asarray(xlen, np.int64) * np.asarray(ylen)))
-    # a sample of about target_s seconds: batches of at most 2048 pairs, repeated
+    # a sample of about target_s seconds: one batch of at most 1024 pairs (generated once,
+    # outside the timed part), swept repeatedly
     want = max(cores, target_s * rate / per_pair)
-    Bs = int(min(2048, want))
+    Bs = int(min(1024, want))
     Bs = max(cores, (Bs // cores) * cores)
     reps = max(1, int(round(want / Bs)))
+    batch = make(Bs)
     cells = 0
     dt = 0.0
     for _ in range(reps):
-        c1, d1 = run(Bs)
+        c1, d1 = run(batch)
         cells += c1
         dt += d1
     return cells / dt, cores, f"{reps} x {Bs} pairs of the workload ({cells} cells), fwd+bwd, {dt:.1f} s", dt
