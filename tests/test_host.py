@@ -176,3 +176,22 @@ def test_bench_affinity_helper_never_raises():
     sys.path.insert(0, ROOT)
     import bench
     assert isinstance(bench.bind_to_gpu_numa_node(0), str)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU port on the host cores) prints one JSON line with
+    the keys the driver reads; under torchrun only rank 0 prints."""
+    import json
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-seconds", "0.5"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "cell-updates/s"
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"] and d["metric"].startswith("DP cell-updates/sec")
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-seconds", "0.5"], capture_output=True, text=True, env=env, timeout=60)
+    assert out.returncode == 0 and out.stdout.strip() == ""
