@@ -2,10 +2,12 @@
  * b200dp.h -- C ABI of libb200dp.so: the B200 (sm_100a) soft-DP alignment engine.
  *
  * One export per Numba-CUDA kernel of the reference (deepblast/nw_cuda.py,
- * deepblast/sw_cuda.py @ ec661fa); a reference maintainer binds these with ctypes
- * from the torch.autograd.Functions.  Plain pointers and
- * sizes only; all device memory is owned by the caller (torch's allocator); the
- * library never allocates, frees or retains device memory and never synchronises.
+ * deepblast/sw_cuda.py @ ec661fa), plus the chained adjoint pair, the host-buffer decode,
+ * the fused MatrixCrossEntropy and the batched traceback; a reference maintainer binds
+ * these with ctypes from the torch.autograd.Functions.  Plain
+ * pointers and sizes only; all device memory is owned by the caller (torch's allocator);
+ * the library never allocates, frees or retains device memory and never synchronises
+ * (b200dp_decode_host owns three internal streams and their events, nothing else).
  * Every launch goes to the CUDA stream passed in (cudaStream_t as void*).
  *
  * Return value: 0 on success, negative for argument errors, positive
@@ -16,15 +18,17 @@
  *   E, Ed, Ztheta  [B, N+2, M+2]    contiguous row-major (padded lattice, nw.py:347)
  *   Vt, Vtd        [B]
  *   Q, Qd          the reference's [B, N+2, M+2, 3] (nw.py:105) stored STRIP-MAJOR, in the
- *                  order the wavefront produces it: lattice cell (i, j) (1-based), state
- *                  s lives at
- *                    b*pair_stride + k*strip_stride + ((j-1) + t)*96 + s*32 + t,
+ *                  order the wavefront produces it, TWO of the three states per cell (x and
+ *                  y of deepblast/constants.py:1; the m state is implied: q_m = 1 - q_x - q_y,
+ *                  qd_m = -(qd_x + qd_y); q_x = -1 marks a cell whose Q is identically zero):
+ *                  lattice cell (i, j) (1-based), stored state c (0 = x, 1 = y) lives at
+ *                    b*pair_stride + k*strip_stride + ((j-1) + t)*64 + c*32 + t,
  *                    k = (i-1)/32, t = (i-1)%32,
- *                  with strip_stride = M*96, pair_stride = ceil(N/32)*strip_stride + 31*96
+ *                  with strip_stride = M*64, pair_stride = ceil(N/32)*strip_stride + 31*64
  *                  (b200dp_q_layout()).  Border cells are implicit (zeros, and
  *                  Q[N+1,M+1,:] = 1) and not stored.  The pointer passed is the storage
  *                  base (16-byte aligned); the allocation must be B*pair_stride + pad
- *                  floats.  State order x=0, m=1, y=2 (deepblast/constants.py:1).
+ *                  floats.
  *   xlen, ylen     optional int32[B] per-pair lattice sizes (1 <= n <= N,
  *                  1 <= m <= M); NULL = every pair is N x M.  With lengths, each
  *                  pair is computed exactly as the reference computes the slice
