@@ -44,6 +44,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return s;
 }
 
+// One CTA per pair; warp w takes rows w, w + 8, ...; lanes stride the columns, so every
+// access is a coalesced 128-byte piece and no index needs a division.
 __global__ void __launch_bounds__(256) softdp_mxent_fwd_kernel(LossParams p) {
     __shared__ float red[8];
     const int b = blockIdx.x;
@@ -52,16 +54,19 @@ __global__ void __launch_bounds__(256) softdp_mxent_fwd_kernel(LossParams p) {
     const float* yt = p.Ytrue + (long long)b * p.N * p.M;
     const float* gm = p.G ? p.G + (long long)b * p.N * p.M : nullptr;
     const float* yp = p.Ypred + (long long)b * p.pb;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     float s = 0.f, c = 0.f;
-    const long long total = (long long)n * m;
-    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
-        const int i = (int)(e / m), j = (int)(e - (long long)i * m);
-        const long long o = (long long)i * p.M + j;
-        if (!gm || gm[o] != 0.f) {
-            const float y = yt[o];
-            const float q = fminf(fmaxf(yp[(long long)i * p.pi + j], kLossEps), kLossMax);
-            s += y * logf(q) + (1.f - y) * logf(1.f - q);
-            c += 1.f;
+    for (int i = w; i < n; i += nw) {
+        const float* ytr = yt + (long long)i * p.M;
+        const float* gmr = gm ? gm + (long long)i * p.M : nullptr;
+        const float* ypr = yp + (long long)i * p.pi;
+        for (int j = lane; j < m; j += 32) {
+            if (!gmr || gmr[j] != 0.f) {
+                const float y = ytr[j];
+                const float q = fminf(fmaxf(ypr[j], kLossEps), kLossMax);
+                s += y * logf(q) + (1.f - y) * logf(1.f - q);
+                c += 1.f;
+            }
         }
     }
     s = block_sum(s, red);
@@ -81,19 +86,24 @@ __global__ void __launch_bounds__(256) softdp_mxent_bwd_kernel(LossParams p) {
     const float* yp = p.Ypred + (long long)b * p.pb;
     float* gr = p.grad + (long long)b * p.N * p.M;
     const float scale = -p.gout[0] / (p.pair_count[b] * (float)p.B);
-    const long long total = (long long)p.N * p.M;
-    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
-        const int i = (int)(e / p.M), j = (int)(e - (long long)i * p.M);
-        float g = 0.f;
-        if (i < n && j < m && (!gm || gm[e] != 0.f)) {
-            const float q0 = yp[(long long)i * p.pi + j];
-            // clamp passes the gradient only inside [eps, max] (torch.clamp backward)
-            if (q0 >= kLossEps && q0 <= kLossMax) {
-                const float y = yt[e];
-                g = scale * (y / q0 - (1.f - y) / (1.f - q0));
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = w; i < p.N; i += nw) {
+        const float* ytr = yt + (long long)i * p.M;
+        const float* gmr = gm ? gm + (long long)i * p.M : nullptr;
+        const float* ypr = yp + (long long)i * p.pi;
+        float* grr = gr + (long long)i * p.M;
+        for (int j = lane; j < p.M; j += 32) {
+            float g = 0.f;
+            if (i < n && j < m && (!gmr || gmr[j] != 0.f)) {
+                const float q0 = ypr[j];
+                // clamp passes the gradient only inside [eps, max] (torch.clamp backward)
+                if (q0 >= kLossEps && q0 <= kLossMax) {
+                    const float y = ytr[j];
+                    g = scale * (y / q0 - (1.f - y) / (1.f - q0));
+                }
             }
+            grr[j] = g;
         }
-        gr[e] = g;
     }
 }
 
