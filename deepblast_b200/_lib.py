@@ -1,6 +1,7 @@
 """ctypes binding of libb200dp.so (include/b200dp.h).  Fails loudly when the
 library is missing: there is no CPU or PyTorch fallback on this path."""
 import ctypes
+import functools
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -55,8 +56,10 @@ def check(rc, what):
         raise RuntimeError(f"{what} failed ({rc}): {msg}")
 
 
+@functools.lru_cache(maxsize=256)
 def q_layout(N, M):
-    """(K strips per pair, strip_stride, pair_stride, tail pad) in floats."""
+    """(K strips per pair, strip_stride, pair_stride, tail pad) in floats (a pure function
+    of the lattice size, asked several times per call: cached)."""
     K = _i()
     ss, ps, pad = _ll(), _ll(), _ll()
     check(lib().b200dp_q_layout(N, M, ctypes.byref(K), ctypes.byref(ss), ctypes.byref(ps),
