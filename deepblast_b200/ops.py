@@ -83,9 +83,8 @@ def _as_engine_q(Q, N=None, M=None, kind="q"):
 def q_from_reference(Qref, kind="q"):
     """Dense reference-layout Q (kind 'q') or Qd (kind 'qd') [B,N+2,M+2,3] -> engine layout
     (5-D view).  The m state is dropped: it must be 1 - x - y for Q (a softmax; all-zero
-    cells are kept as marks) and -(x + y) for Qd."""
-    if not Qref.is_cuda:
-        raise RuntimeError("Q must be a CUDA tensor")
+    cells are kept as marks) and -(x + y) for Qd.  A pure layout conversion (torch indexing
+    only): it also runs on CPU tensors, which is how the layout is tested without a GPU."""
     B, N2, M2, _ = Qref.shape
     N, M = N2 - 2, M2 - 2
     Q5 = q_empty(B, N, M, Qref.device)

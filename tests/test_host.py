@@ -195,3 +195,36 @@ def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "0", "--cpu-seconds", "0.5"], capture_output=True, text=True, env=env, timeout=60)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+@pytest.mark.parametrize("name", ["r8x8", "r17x23", "r33x40", "r64x48"])
+def test_strip_major_two_state_layout_round_trip_on_cpu(golden, name, mode):
+    """The engine's Q layout (two stored states, implied m state, zero marks) against the
+    reference-generated golden Q / Qd: conversion there and back on CPU tensors, element
+    addresses as documented in include/b200dp.h."""
+    from deepblast_b200 import _lib, ops
+    Qref = torch.from_numpy(golden[f"{name}/{mode}/Q"])
+    B, N2, M2, _ = Qref.shape
+    N, M = N2 - 2, M2 - 2
+    Q5 = ops.q_from_reference(Qref)
+    K, ss, ps, pad = _lib.q_layout(N, M)
+    assert tuple(Q5.shape) == (B, K, 32, M, 2) and tuple(Q5.stride()) == (ps, ss, 65, 64, 32)
+    flat = Q5.as_strided((B * ps + pad,), (1,))                # the raw storage
+    for (b, i, j) in [(0, 1, 1), (B - 1, N, M), (0, min(N, 33), 2), (B - 1, 2, M)]:
+        k, t = (i - 1) // 32, (i - 1) % 32
+        base = b * ps + k * ss + ((j - 1) + t) * 64 + t
+        x, m, y = Qref[b, i, j].tolist()
+        if x == 0 and m == 0 and y == 0:                         # sw.py first row / column: the mark
+            assert flat[base].item() < 0
+        else:
+            assert flat[base].item() == x and flat[base + 32].item() == min(y, np.float32(1) - np.float32(x))
+    back = ops.q_to_reference(Q5, N)
+    np.testing.assert_array_equal(back[..., 0].numpy(), Qref[..., 0].numpy())
+    np.testing.assert_allclose(back.numpy(), Qref.numpy(), rtol=0, atol=2e-7)
+    assert np.array_equal((back.sum(-1) == 0).numpy(), (Qref.sum(-1) == 0).numpy())
+    assert float(back.min()) >= 0.0                                # the implied state never goes negative
+    Qd = torch.from_numpy(golden[f"{name}/{mode}/Qd"])
+    backd = ops.q_to_reference(ops.q_from_reference(Qd, "qd"), N, "qd")
+    scale = max(1.0, float(Qd.abs().max()))
+    np.testing.assert_allclose(backd[:, 1:-1, 1:-1].numpy(), Qd[:, 1:-1, 1:-1].numpy(), rtol=0, atol=2e-6 * scale)
