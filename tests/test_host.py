@@ -228,3 +228,22 @@ def test_strip_major_two_state_layout_round_trip_on_cpu(golden, name, mode):
     backd = ops.q_to_reference(ops.q_from_reference(Qd, "qd"), N, "qd")
     scale = max(1.0, float(Qd.abs().max()))
     np.testing.assert_allclose(backd[:, 1:-1, 1:-1].numpy(), Qd[:, 1:-1, 1:-1].numpy(), rtol=0, atol=2e-6 * scale)
+
+
+def test_header_is_plain_c_and_bindings_match_it(tmp_path):
+    """include/b200dp.h compiles as C (the boundary is a C ABI), and every ctypes binding in
+    deepblast_b200/_lib.py has as many arguments as the declaration it binds."""
+    from deepblast_b200 import _lib
+    hdr_path = os.path.join(ROOT, "include", "b200dp.h")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "b200dp.h"\nint main(void) { int (*f)(void) = b200dp_version; const char* (*g)(void) = b200dp_last_error; return f == 0 || g == 0; }\n')
+    r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only",
+                        "-I", os.path.dirname(hdr_path), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    hdr = re.sub(r"/\*.*?\*/", "", open(hdr_path).read(), flags=re.S)
+    decls = dict(re.findall(r"\b(b200dp_[a-z_0-9]+)\s*\(([^;{]*)\)\s*;", hdr))
+    assert set(decls) == set(_lib.EXPORTS)
+    for name, args in decls.items():
+        args = args.strip()
+        n = 0 if args in ("", "void") else len(args.split(","))
+        assert n == len(_lib.EXPORTS[name][1]), (name, n, len(_lib.EXPORTS[name][1]))
