@@ -10,6 +10,7 @@ are stored; the m state is implied (Q sums to 1 over the states, Qd to 0), and q
 marks a cell whose Q is identically zero (first row / column of the sw.py lattice).
 """
 import ctypes
+import threading
 
 import torch
 
@@ -284,6 +285,7 @@ def traceback_batch(grad, xlen=None, ylen=None, variant="cuda"):
 
 
 _host_ws = {}
+_host_ws_lock = threading.Lock()
 
 
 def decode_host(theta_h, A_h, mode="nw", Et_h=None, chunk_pairs=None, out=None, device=None, flags=0):
@@ -291,8 +293,7 @@ def decode_host(theta_h, A_h, mode="nw", Et_h=None, chunk_pairs=None, out=None, 
     HOST tensors (pinned for full PCIe speed) -> (Vt_h [B], grad_h [B,N,M]) pinned host
     tensors, grad_h = dVt/dtheta being a view of the padded E the engine downloads.
     Uploads, sweeps and downloads of consecutive chunks overlap (b200dp_decode_host).
-    Returns after the results have landed unless `out` is given with sync=False semantics
-    handled by the caller (see `decode_host_async`)."""
+    Returns after the results have landed; `decode_host_async` only enqueues."""
     Vt_h, E_h = decode_host_async(theta_h, A_h, mode, Et_h, chunk_pairs, out, device, flags)
     torch.cuda.current_stream(device).synchronize()
     return Vt_h, E_h[:, 1:-1, 1:-1]
@@ -322,11 +323,12 @@ def decode_host_async(theta_h, A_h, mode="nw", Et_h=None, chunk_pairs=None, out=
     with torch.cuda.device(dev):
         need = _lib.lib().b200dp_decode_host_workspace(N, M, chunk_pairs)
         key = (dev.index, N, M, chunk_pairs)
-        ws = _host_ws.get(key)
-        if ws is None or ws.numel() < need:
-            _host_ws.clear()                       # one cached workspace per process is enough
-            ws = torch.empty(need, dtype=torch.uint8, device=dev)
-            _host_ws[key] = ws
+        with _host_ws_lock:
+            ws = _host_ws.get(key)
+            if ws is None or ws.numel() < need:
+                _host_ws.clear()                   # one cached workspace per process is enough
+                ws = torch.empty(need, dtype=torch.uint8, device=dev)
+                _host_ws[key] = ws
         if out is None:
             Vt_h = torch.empty(B, dtype=torch.float32, pin_memory=True)
             E_h = torch.empty((B, N + 2, M + 2), dtype=torch.float32, pin_memory=True)
