@@ -17,13 +17,29 @@ from . import ops
 def make_classes(mode, prefix):
     class FunctionBackward(torch.autograd.Function):
         @staticmethod
-        def forward(ctx, theta, A, Et, Q, operator, interior=False, keep_interior=False):
+        def forward(ctx, theta, A, Et, Q, operator, interior=False, keep_interior=False, plan=None):
             # `interior` (not part of the reference's signature, nw_cuda.py:212): return
             # E[:, 1:-1, 1:-1] instead of the padded E, so that the double backward receives the
-            # gradient of the interior directly instead of a zero-padded copy it would slice again
+            # gradient of the interior directly instead of a zero-padded copy it would slice again.
+            # `plan` (ours as well): the batch runs on the strip-queue kernels (ops.sq_*), whose E
+            # IS the interior, in the plan's layout (dense [B, N, M] or a flat packed buffer).
             if operator != 'softmax':
                 raise NotImplementedError(
                     "CUDA variant only supports 'softmax' operator")
+            ctx.set_materialize_grads(False)
+            ctx.others = operator
+            ctx.interior = bool(interior)
+            ctx.plan = plan
+            if plan is not None:
+                E = ops.sq_backward(plan, Et, Q, mode)
+                ctx.save_for_backward(Q, E, None)
+                ctx.lens = (None, None)
+                if interior or plan.packed:
+                    return E, A
+                Epad = torch.zeros((plan.B, plan.N + 2, plan.M + 2), dtype=E.dtype, device=E.device)
+                Epad[:, 1:-1, 1:-1] = E
+                Epad[:, plan.N + 1, plan.M + 1] = Et           # nw.py:125-127
+                return Epad, A
             lens = getattr(Q, "_b200dp_lens", (None, None))
             # Q: the engine's strip-major view (from our forward) or a dense
             # reference-layout [B,N+2,M+2,3] tensor (converted on the fly)
@@ -37,16 +53,24 @@ def make_classes(mode, prefix):
             else:
                 E, Ei = ops.backward_pass(Et, Q, mode, lens[0], lens[1], N=theta.shape[1]), None
             # an unused output gradient arrives as None, not as a tensor of zeros to be read
-            ctx.set_materialize_grads(False)
             ctx.save_for_backward(Q, E, Ei)
-            ctx.others = operator
             ctx.lens = lens
-            ctx.interior = bool(interior)
             return (E[:, 1:-1, 1:-1] if interior else E), A
 
         @staticmethod
         def backward(ctx, Ztheta, ZA):
             Q, E, Ei = ctx.saved_tensors
+            plan = ctx.plan
+            if plan is not None:
+                if Ztheta is None:
+                    Zt = torch.zeros_like(E)
+                elif ctx.interior or plan.packed:
+                    Zt = Ztheta
+                else:
+                    Zt = Ztheta[:, 1:-1, 1:-1]
+                Vtd, QdE = ops.sq_adjoint_forward(plan, Q, Zt, ZA, E)
+                Ed = ops.sq_adjoint_backward(plan, Q, QdE)
+                return Ed, None, Vtd, None, None, None, None, None
             xl, yl = ctx.lens
             if xl is None and yl is None and (Ztheta is None or Ztheta.dtype == torch.float32):
                 # large batches of equal-size lattices: both sweeps on the chained kernels
@@ -71,17 +95,30 @@ def make_classes(mode, prefix):
 
     class Function(torch.autograd.Function):
         @staticmethod
-        def forward(ctx, theta, A, operator, xlen=None, ylen=None):
+        def forward(ctx, theta, A, operator, xlen=None, ylen=None, plan=None):
+            # xlen / ylen / plan are ours (the reference's forward takes theta, A, operator,
+            # nw_cuda.py:170): per-pair lattice sizes, and an explicit plan.Plan (required for the
+            # packed layout, where theta and A are flat buffers)
             if operator != 'softmax':
                 raise NotImplementedError(
                     "CUDA variant only supports 'softmax' operator")
             if theta.dtype != torch.float32:
                 raise TypeError("CUDA variant only supports torch.float32 type")
+            if plan is None:
+                plan = ops.route_plan(theta, xlen, ylen)
+            ctx.plan = plan
+            ctx.others = operator
+            if plan is not None:
+                # no Q when nothing can ask for a gradient (NeuralAligner.score, alignment.py:127-137)
+                need_q = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+                Vt, Q = ops.sq_forward(plan, theta, A, mode, need_q=need_q)
+                ctx.save_for_backward(theta, A, Q)
+                ctx.lens = (None, None)
+                return Vt
             Vt, Q = ops.forward_pass(theta, A, mode, xlen, ylen)
             if xlen is not None or ylen is not None:
                 Q._b200dp_lens = (xlen, ylen)
             ctx.save_for_backward(theta, A, Q)
-            ctx.others = operator
             ctx.lens = (xlen, ylen)
             return Vt
 
@@ -89,20 +126,23 @@ def make_classes(mode, prefix):
         def backward(ctx, Et):
             theta, A, Q = ctx.saved_tensors
             operator = ctx.others
+            if ctx.plan is not None:
+                E, A = FunctionBackward.apply(theta, A, Et, Q, operator, True, False, ctx.plan)
+                return E, A, None, None, None, None
             if ctx.lens != (None, None):
                 Q._b200dp_lens = ctx.lens
             E, A = FunctionBackward.apply(theta, A, Et, Q, operator, True, torch.is_grad_enabled())
-            return E, A, None, None, None
+            return E, A, None, None, None, None
 
     class Decoder(nn.Module):
         def __init__(self, operator):
             super().__init__()
             self.operator = operator
 
-        def forward(self, theta, A, xlen=None, ylen=None):
-            if xlen is None and ylen is None:
+        def forward(self, theta, A, xlen=None, ylen=None, plan=None):
+            if xlen is None and ylen is None and plan is None:
                 return Function.apply(theta, A, self.operator)
-            return Function.apply(theta, A, self.operator, xlen, ylen)
+            return Function.apply(theta, A, self.operator, xlen, ylen, plan)
 
         def traceback(self, grad):
             """Greedy walk over one [N, M] expected-alignment matrix; the rule of
@@ -117,10 +157,11 @@ def make_classes(mode, prefix):
             """All pairs of a [B, N, M] batch in one launch."""
             return ops.traceback_batch(grad, xlen, ylen, variant)
 
-        def decode(self, theta, A, xlen=None, ylen=None):
-            """ Shortcut for doing inference. """
+        def decode(self, theta, A, xlen=None, ylen=None, plan=None):
+            """ Shortcut for doing inference.  (xlen / ylen: per-pair lattice sizes; plan: a
+            plan.Plan, e.g. a packed one -- theta, A and the result are then flat packed buffers.) """
             with torch.enable_grad():
-                nll = self.forward(theta, A, xlen, ylen)
+                nll = self.forward(theta, A, xlen, ylen, plan)
                 v = torch.sum(nll)
                 v_grad, _ = torch.autograd.grad(v, (theta, A), create_graph=True)
             return v_grad

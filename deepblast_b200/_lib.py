@@ -31,6 +31,15 @@ EXPORTS = {
     "b200dp_mxent_fwd": (ctypes.c_int, [_f, _f, _ll, _ll, _f, _f, _f, _i, _i, _i, _f, _f, _f]),
     "b200dp_mxent_bwd": (ctypes.c_int, [_f, _f, _ll, _ll, _f, _f, _f, _i, _i, _i, _f, _f, _f, _f]),
     "b200dp_traceback": (ctypes.c_int, [_f, _ll, _ll, _ll, _f, _f, _i, _i, _i, _i, _f, _i, _f, _f]),
+    # strip-queue family (plan builder is host code: works without a GPU)
+    "b200dp_plan_build": (ctypes.c_int, [_f, _f, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f, _i]),
+    "b200dp_sq_workspace_bytes": (ctypes.c_size_t, [_ll]),
+    "b200dp_sq_resident_warps": (ctypes.c_int, [_i]),
+    "b200dp_sq_set_trace": (None, [_f]),
+    "b200dp_sq_fwd": (ctypes.c_int, [_f, _i, _f, ctypes.c_uint, _f, _f, _f, _f, _i, _i, _f]),
+    "b200dp_sq_bwd": (ctypes.c_int, [_f, _i, _f, ctypes.c_uint, _f, _ll, _f, _f, _i, _i, _f]),
+    "b200dp_sq_adj_fwd": (ctypes.c_int, [_f, _i, _f, ctypes.c_uint, _f, _f, _f, _f, _f, _f, _i, _f]),
+    "b200dp_sq_adj_bwd": (ctypes.c_int, [_f, _i, _f, ctypes.c_uint, _f, _f, _f, _i, _f]),
 }
 
 

@@ -12,6 +12,7 @@
 #include <string>
 
 #include "../../include/b200dp.h"
+#include "softdp_host.h"
 #include "softdp_adjoint.cuh"
 #include "softdp_bwd.cuh"
 #include "softdp_bwd2.cuh"
@@ -23,19 +24,9 @@
 #include "softdp_traceback.cuh"
 
 using namespace b200dp;
+using namespace b200dp_host;
 
 namespace {
-
-thread_local std::string g_err;
-
-int fail(int code, const std::string& msg) {
-    g_err = msg;
-    return code;
-}
-int cuda_fail(cudaError_t e, const char* what) {
-    g_err = std::string(what) + ": " + cudaGetErrorString(e);
-    return (int)e;
-}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -54,38 +45,12 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-struct DevInfo {
-    int sms = 0;
-    int smem_optin = 0;
-    int smem_per_sm = 0;
-};
-
-bool dev_info(DevInfo& out) {
-    static DevInfo cache[64];
-    static bool have[64] = {false};
-    static std::mutex mu;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
-    std::lock_guard<std::mutex> lk(mu);
-    if (!have[dev]) {
-        DevInfo d;
-        if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
-        cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        cudaDeviceGetAttribute(&d.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-        cache[dev] = d;
-        have[dev] = true;
-    }
-    out = cache[dev];
-    return true;
-}
-
 // The chained kernels run one warp per pair: their time is one pair's latency, flat up to ~7
 // pairs per SM, while the hand-off kernels (W warps per pair) scale with the batch.  Measured
 // on B200 the two meet at about 4 pairs per SM (256 x 256: forward 0.177 ms chained against
 // 0.085 ms hand-off at 2 pairs per SM).
 constexpr int kChainedMinPairsPerSM = 4;
 
-bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // rank-3 map over a contiguous [B, N, M] fp32 tensor, box 32 cols x 32 rows x 1
 bool encode_row_map(CUtensorMap* map, const float* ptr, int B, int N, int M, int boxdim = kTile, int boxrows = 0) {
@@ -194,28 +159,6 @@ int pick_geometry(const char* fn, int B, int N, int M, int flags, SmemFn smem_of
     }
     if (!g.W) return fail(-3, std::string(fn) + ": M too large for shared memory boundary rows");
     if (forceG > 0) g.grid = forceG;
-    return 0;
-}
-
-// cudaFuncSetAttribute is not free (and may serialise with work in flight): remember,
-// per device and kernel, the largest dynamic shared-memory size already granted.
-template <class Kern>
-int set_smem(Kern k, size_t smem, const char* fn) {
-    static std::mutex mu;
-    static std::map<std::pair<int, const void*>, size_t> granted;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const std::pair<int, const void*> key(dev, reinterpret_cast<const void*>(k));
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        auto it = granted.find(key);
-        if (it != granted.end() && it->second >= smem) return 0;
-    }
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, fn);
-    std::lock_guard<std::mutex> lk(mu);
-    size_t& g = granted[key];
-    if (g < smem) g = smem;
     return 0;
 }
 

@@ -70,14 +70,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// A wait that cannot complete is a protocol bug: trap (the launch fails with an error
-// the host sees) instead of hanging the device.
-constexpr unsigned kSpinLimit = 1u << 22;
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    unsigned spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > kSpinLimit) __trap();
+// A wait that cannot complete is a protocol bug.  Release builds wait on wall-clock time, not
+// on a poll count (a legitimate wait under preemption, MPS time-slicing, a debugger or ncu
+// replay may take many polls): the launch is only failed (trap: the host sees an error instead
+// of a hung device) after kWaitLimitNs of real time; -DB200DP_NO_WAIT_LIMIT compiles the bound out.
+constexpr unsigned long long kWaitLimitNs = 8000000000ull;      // 8 s
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+struct WaitGuard {
+    unsigned polls = 0;
+    unsigned long long t0 = 0;
+    // call once per failed poll; cheap until the wait has lasted a few thousand polls
+    __device__ __forceinline__ void tick() {
+#ifndef B200DP_NO_WAIT_LIMIT
+        if ((++polls & 0x3ffu) == 0) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kWaitLimitNs) __trap();
+        }
+#endif
     }
+};
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    WaitGuard g;
+    while (!mbar_try_wait(bar, parity)) g.tick();
 }
 
 // One lane of a converged warp, known to the compiler to be exactly one (elect.sync):
@@ -136,6 +156,16 @@ __device__ __forceinline__ void cp_async4_zfill(void* dst, const void* src, bool
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+// 16-byte copy with a 256-byte L2 prefetch hint; !valid zero-fills the destination (nothing is read)
+__device__ __forceinline__ void cp_async16_zfill_l2(void* dst, const void* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(valid ? 16 : 0)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -147,6 +177,22 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.acquire.cta.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+// ---- cross-CTA hand-off words (coherent at GPU scope, i.e. served by L2; no fences: the
+// payload and its validity tag travel in ONE 8-byte word, see softdp_sq.cuh) -------------------
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// the same hand-off as a reduction performed AT the L2 (never parked in an SM-side write buffer):
+// tags grow from launch to launch, so max() replaces whatever an earlier launch left behind
+__device__ __forceinline__ void red_max_gpu_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -251,7 +297,10 @@ __device__ __forceinline__ void strip_next(Strip& s, const PairDims& d, int w, i
 
 // wait until boundary `q` has published at least `need` entries
 __device__ __forceinline__ int progress_wait(const unsigned long long* word, unsigned q, int need) {
+#ifdef B200DP_DEBUG_WAIT
     unsigned spins = 0;
+#endif
+    WaitGuard g;
     for (;;) {
         unsigned long long v = ld_acquire_u64(word);
         if ((unsigned)(v >> 32) == q && (int)(unsigned)v >= need) return (int)(unsigned)v;
@@ -264,7 +313,7 @@ __device__ __forceinline__ int progress_wait(const unsigned long long* word, uns
             return need;
         }
 #else
-        if (++spins > kSpinLimit) __trap();
+        g.tick();
 #endif
     }
 }
@@ -281,10 +330,10 @@ __device__ __forceinline__ void strip_gate(const unsigned long long* fin, unsign
     if (W > 1 && q >= (unsigned)(W + 1)) {
         const unsigned long long* f = fin + ((w + W - 1) % W);
         const unsigned long long want = (unsigned long long)q - (unsigned)W;      // 1 + (q - (W+1))
-        unsigned spins = 0;
+        WaitGuard g;
         while (ld_acquire_u64(f) < want) {
             __nanosleep(32);
-            if (++spins > kSpinLimit) __trap();
+            g.tick();
         }
     }
 }

@@ -46,7 +46,8 @@ __host__ __device__ inline size_t fwd2_smem_bytes(int W, int M) {
 // lattice-membership predicates and the zero border cells; SWM adds the sw.py i, j >= 2
 // rule.  hup = h of the row above at this column, v = the lane's own vertical difference
 // at the previous column (in), this column (out); returns h of this cell.
-// DBG (diagnostic builds only): bit 0 = drop the Q stores, bit 1 = no theta/A staging.
+// DBG: bit 0 = drop the Q stores but keep the arithmetic, bit 1 = no theta/A staging (both
+// diagnostic builds only); bit 2 = score-only forward (no Q at all).
 template <bool EDGE, bool SWM, int DBG = 0>
 __device__ __forceinline__ float fwd2_step(float th, float a, float hup, float& v, float* __restrict__ qp,
                                            bool store, bool comp) {
@@ -81,7 +82,10 @@ __device__ __forceinline__ float fwd2_step(float th, float a, float hup, float& 
             qy = comp ? qy : kQZeroMark;
         }
     }
-    if (DBG & 1) {
+    if (DBG & 4) {
+        // score-only forward (Vt alone, deepblast/alignment.py:127-137 under no_grad): no Q is
+        // written and the compiler drops the probability arithmetic with the stores
+    } else if (DBG & 1) {
         if (qx + qy == 12345.f) qp[0] = qx;          // keeps the math alive, never true
     } else if (!EDGE || store) {
         qp[0] = qx;

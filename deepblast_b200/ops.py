@@ -251,6 +251,139 @@ def adjoint_pair_fast(Q, E, Ztheta, ZA=None, N=None, flags=0, interior=False, Ei
     return Vtd, (Edi if interior_out else Ed)
 
 
+# ---- strip-queue family: any batch shape, dense or packed (csrc/softdp_sq.cuh) ---------------
+SQ_RING_SHIFT = 24
+CTAS_SHIFT = 8
+
+
+def _sq_ws(plan, t):
+    from . import plan as _plan
+    stream = _stream(t)
+    ws, epoch = _plan.workspace(t.device, stream, plan.ws_bytes)
+    return ws, epoch, stream
+
+
+def _sq_check_operand(name, t, plan):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (deepblast_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise TypeError("CUDA variant only supports torch.float32 type")
+    if t.numel() < plan.packed_floats:
+        raise RuntimeError(f"{name}: {t.numel()} elements, the plan's layout needs {plan.packed_floats}")
+    if t.device != plan.device:
+        raise RuntimeError(f"{name} is on {t.device}, the plan was built for {plan.device}")
+
+
+# Which batches the autograd functions send to the strip-queue kernels when the caller gave no
+# plan: "auto" (ragged batches, and equal-size batches too small for the chained kernels),
+# "always" (every shape the kernels take), "never" (the round-1 kernels only).
+SQ_MODE = "auto"
+_sm_count = {}
+
+
+def route_plan(theta, xlen=None, ylen=None):
+    """The plan.Plan the batch should run with, or None for the chained / hand-off / general kernels."""
+    from . import plan as _plan
+    if SQ_MODE == "never" or not theta.is_cuda or theta.dim() != 3:
+        return None
+    B, N, M = theta.shape
+    if B == 0 or M % 4 != 0:
+        return None
+    if SQ_MODE == "auto" and xlen is None and ylen is None:
+        sms = _sm_count.get(theta.device.index)
+        if sms is None:
+            sms = _sm_count[theta.device.index] = torch.cuda.get_device_properties(theta.device).multi_processor_count
+        if B >= 4 * sms and N >= 32 and M >= 64 and M % 32 == 0:
+            return None                      # large equal-size batch: the chained kernels
+    return _plan.get_plan(B, N, M, xlen, ylen, False, theta.device)
+
+
+def sq_forward(plan, theta, A, mode="nw", need_q=True, flags=0):
+    """theta, A in the plan's layout (dense [B,N,M] or a flat packed buffer) -> (Vt [B], Q flat
+    strip-major buffer, or None with need_q=False: score only).  nw.py:65-117 per pair."""
+    theta = theta.detach().contiguous()
+    A = A.detach().contiguous()
+    _sq_check_operand("theta", theta, plan)
+    _sq_check_operand("A", A, plan)
+    with torch.cuda.device(theta.device):
+        Q = torch.empty(plan.q_floats, dtype=torch.float32, device=theta.device) if need_q else None
+        alloc = torch.zeros if plan.has_empty else torch.empty      # an empty pair scores 0 (nothing to sum)
+        Vt = alloc(plan.B, dtype=torch.float32, device=theta.device)
+        ws, epoch, stream = _sq_ws(plan, theta)
+        rc = _lib.lib().b200dp_sq_fwd(_ptr(plan.fwd_tab), plan.nstrips, _ptr(ws), epoch, _ptr(theta), _ptr(A),
+                                      _ptr(Q), _ptr(Vt), MODES[mode], flags, stream)
+        _lib.check(rc, "b200dp_sq_fwd")
+    return Vt, Q
+
+
+def _sq_out_like(plan, ref):
+    """E / Ed in the plan's operand layout.  Dense ragged batches must read as zero outside each
+    pair's corner (the gradient of cells the pair does not have); packed buffers have no such cells
+    except the few pitch-padding floats per row, zeroed too so that sums over the buffer are exact."""
+    if plan.packed:
+        return torch.zeros(plan.packed_floats, dtype=torch.float32, device=ref.device)
+    alloc = torch.zeros if plan.ragged else torch.empty
+    return alloc((plan.B, plan.N, plan.M), dtype=torch.float32, device=ref.device)
+
+
+def sq_backward(plan, Et, Q, mode="nw", flags=0):
+    """Et [B] (any stride), Q (flat, from sq_forward) -> E in the plan's layout: the INTERIOR of
+    the reference's padded E (nw.py:138-175, 339), i.e. dVt/dtheta."""
+    _check_in("Et", Et, (plan.B,))
+    Et = Et.detach()
+    with torch.cuda.device(Q.device):
+        E = _sq_out_like(plan, Q)
+        ws, epoch, stream = _sq_ws(plan, Q)
+        rc = _lib.lib().b200dp_sq_bwd(_ptr(plan.bwd_tab), plan.nstrips, _ptr(ws), epoch, _ptr(Et),
+                                      Et.stride(0) if plan.B > 0 else 0, _ptr(Q), _ptr(E), MODES[mode], flags, stream)
+        _lib.check(rc, "b200dp_sq_bwd")
+    return E
+
+
+def sq_adjoint_forward(plan, Q, Zt, ZA=None, E=None, flags=0):
+    """Q, Zt (the interior of Ztheta, plan layout), ZA (plan layout) or None, E (plan layout) or
+    None -> (Vtd [B], QdE flat: Qd * E, or Qd itself without E).  nw.py:202-248 per pair."""
+    Zt = Zt.detach().contiguous()
+    _sq_check_operand("Ztheta", Zt, plan)
+    if ZA is not None:
+        ZA = ZA.detach().contiguous()
+        _sq_check_operand("ZA", ZA, plan)
+    if E is not None:
+        E = E.detach().contiguous()
+        _sq_check_operand("E", E, plan)
+    with torch.cuda.device(Q.device):
+        QdE = torch.empty(plan.q_floats, dtype=torch.float32, device=Q.device)
+        alloc = torch.zeros if plan.has_empty else torch.empty
+        Vtd = alloc(plan.B, dtype=torch.float32, device=Q.device)
+        ws, epoch, stream = _sq_ws(plan, Q)
+        rc = _lib.lib().b200dp_sq_adj_fwd(_ptr(plan.fwd_tab), plan.nstrips, _ptr(ws), epoch, _ptr(Q), _ptr(Zt),
+                                          _ptr(ZA), _ptr(E), _ptr(Vtd), _ptr(QdE), flags, stream)
+        _lib.check(rc, "b200dp_sq_adj_fwd")
+    return Vtd, QdE
+
+
+def sq_adjoint_backward(plan, Q, QdE, flags=0):
+    """Q, QdE (= Qd * E from sq_adjoint_forward) -> Ed in the plan's layout (the interior of the
+    reference's padded Ed, nw.py:270-312, 386)."""
+    with torch.cuda.device(Q.device):
+        Ed = _sq_out_like(plan, Q)
+        ws, epoch, stream = _sq_ws(plan, Q)
+        rc = _lib.lib().b200dp_sq_adj_bwd(_ptr(plan.bwd_tab), plan.nstrips, _ptr(ws), epoch, _ptr(Q), _ptr(QdE),
+                                          _ptr(Ed), flags, stream)
+        _lib.check(rc, "b200dp_sq_adj_bwd")
+    return Ed
+
+
+def sq_q_to_reference(plan, Q, b, kind="q"):
+    """Pair b of a flat strip-major Q / Qd buffer -> the reference's dense padded
+    [n_b+2, m_b+2, 3] (tests; pure indexing, also runs on CPU tensors)."""
+    n, m = int(plan.xlen[b]), int(plan.ylen[b])
+    K = (n + 31) // 32
+    ss = m * 64
+    v = Q.as_strided((1, K, 32, m, 2), (0, ss, 65, 64, 32), Q.storage_offset() + int(plan.q_off[b]))
+    return q_to_reference(v, n, kind)[0]
+
+
 def traceback_batch(grad, xlen=None, ylen=None, variant="cuda"):
     """grad [B,N,M] (any strides) -> list of B lists of (i, j, state) tuples, exactly
     what NeedlemanWunschDecoder.traceback returns per pair (nw.py:401-444 for

@@ -155,6 +155,77 @@ int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h
                        float* E_h, int B, int N, int M, int mode, int chunk_pairs,
                        void* workspace, size_t workspace_bytes, int flags, void* stream);
 
+/* ---- strip-queue family: batches of any shape -- ragged (per-pair lengths), PACKED, small
+ * batches of long pairs, large batches of equal pairs (softdp_sq.cuh).  Same passes as above
+ * (one export per reference kernel, deepblast/nw_cuda.py:46-165); with per-pair lengths each
+ * pair is computed exactly as the reference computes the slice theta[b, :n_b, :m_b] on its own
+ * (deepblast/alignment.py:165-169).
+ *
+ * b200dp_plan_build (HOST code, no CUDA call) cuts the pairs into strips of 32 rows and writes
+ * the two work-queue tables (forward order, backward order; 64 bytes per strip) that the caller
+ * uploads once per batch and reuses for all four sweeps.  Operand layouts:
+ *   dense  (packed = 0): theta / A / E / Ztheta / Ed are contiguous [B, N, M] (M % 4 == 0), pair
+ *                        b uses the top-left n_b x m_b corner; E / Ed are the INTERIOR of the
+ *                        reference's padded tensors (E_ref[:, 1:-1, 1:-1], nw.py:339): no
+ *                        border is stored, the kernels touch nothing outside a pair's corner;
+ *   packed (packed = 1): one flat buffer, pair b is an n_b x pitch_b row-major block at
+ *                        element offset pair_off[b], pitch_b = (m_b + 3) & ~3 -- the layout of
+ *                        dataset/utils.py:214-251 carried one step further, no padding to the
+ *                        global maximum length at all.
+ * Q / QdE: the strip-major layout described at the top with the pair's own m_b, pair b at float
+ * offset q_off[b] of a buffer of info.q_floats floats.
+ * Lengths outside [0, N] x [0, M] are clamped like the reference's slices; a pair with n_b = 0
+ * or m_b = 0 has no strips (its Vt is not written: zero-fill Vt beforehand).
+ * Call with fwd_tab = bwd_tab = NULL to size the buffers (info), then again to fill them.
+ * warps_fwd / warps_bwd: b200dp_sq_resident_warps() of the forward / backward sweep -- the ticket
+ * order is a list schedule for that many warps (longest remaining dependency chain first, a
+ * strip not before its predecessor is far enough ahead); <= 0 picks a default.
+ *
+ * The launchers take a DEVICE workspace of b200dp_sq_workspace_bytes(info.bnd_words) bytes,
+ * zero-filled ONCE when allocated (the kernels leave it clean) and used by one launch at a time
+ * (launches on one stream are fine), and an `epoch` that differs from launch to launch on the
+ * same workspace and is never 0.  flags: B200DP_CTAS_SHIFT (grid override), B200DP_SQ_RING_SHIFT. */
+#define B200DP_SQ_RING_SHIFT 24    /* bits 24..27: tile ring depth override; 0 = default */
+#define B200DP_SQ_DBG_SHIFT  28    /* bits 28..30: diagnostics (timing experiments; results are wrong when set) */
+
+typedef struct b200dp_plan_info {
+    int nstrips;               /* records per table */
+    int max_m;
+    long long q_floats;        /* floats of a Q / QdE buffer */
+    long long bnd_words;       /* 8-byte words of boundary scratch (b200dp_sq_workspace_bytes) */
+    long long packed_floats;   /* floats of a theta / A / E buffer in this layout */
+    long long cells;           /* sum of n_b * m_b */
+} b200dp_plan_info;
+
+int b200dp_plan_build(const int32_t* xlen, const int32_t* ylen, int B, int N, int M, int packed,
+                      int warps_fwd, int warps_bwd, b200dp_plan_info* info, long long* pair_off,
+                      long long* q_off, void* fwd_tab, void* bwd_tab, int tab_capacity);
+size_t b200dp_sq_workspace_bytes(long long bnd_words);
+/* resident warps of sweep `kind` (0 fwd, 1 bwd, 2 adjoint fwd, 3 adjoint bwd) on the current device */
+int b200dp_sq_resident_warps(int kind);
+
+/* diagnostics: the launches of the calling thread record {start, end} (globaltimer ns) of every
+ * ticket into trace[2 * nstrips] (device memory); NULL switches it off again */
+void b200dp_sq_set_trace(void* trace);
+
+/* _forward_pass_kernel (nw_cuda.py:46-79).  Q = NULL: score only, Vt alone
+ * (deepblast/alignment.py:127-137 calls ddp(theta, A) under no_grad). */
+int b200dp_sq_fwd(const void* fwd_tab, int nstrips, void* workspace, unsigned epoch,
+                  const float* theta, const float* A, float* Q, float* Vt, int mode, int flags,
+                  void* stream);
+/* _backward_pass_kernel (nw_cuda.py:82-102): Et, Q -> E (interior layout). */
+int b200dp_sq_bwd(const void* bwd_tab, int nstrips, void* workspace, unsigned epoch,
+                  const float* Et, long long et_stride, const float* Q, float* E, int mode,
+                  int flags, void* stream);
+/* _adjoint_forward_pass_kernel (nw_cuda.py:105-139): Q, Zt (interior layout), ZA or NULL, E
+ * (interior layout) or NULL -> Vtd, QdE = Qd * E (Qd itself when E is NULL). */
+int b200dp_sq_adj_fwd(const void* fwd_tab, int nstrips, void* workspace, unsigned epoch,
+                      const float* Q, const float* Zt, const float* ZA, const float* E,
+                      float* Vtd, float* QdE, int flags, void* stream);
+/* _adjoint_backward_pass_kernel (nw_cuda.py:142-165): Q, QdE -> Ed (interior layout). */
+int b200dp_sq_adj_bwd(const void* bwd_tab, int nstrips, void* workspace, unsigned epoch,
+                      const float* Q, const float* QdE, float* Ed, int flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
