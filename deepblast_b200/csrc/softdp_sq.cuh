@@ -225,10 +225,15 @@ __global__ void __launch_bounds__(32) softdp_sq_fwd_kernel(const SqParams p) {
         cp_async_mbar_arrive_noinc(&bars[slot]);
     };
 
-    // ---- tickets: the first one is the CTA's index, the rest come from the counter ------------
-    const int G = (int)gridDim.x;
-    StripRec cur = sq_load_rec(p.tab, (int)blockIdx.x, p.nstrips);
-    int cur_tk = (int)blockIdx.x, nxt_tk = 0;
+    // ---- tickets: all from the counter, so that a warp only ever waits for strips that RUNNING
+    // warps hold (no assumption that the whole grid is resident) -----------------------------
+    int cur_tk = 0, nxt_tk = 0;
+    {
+        unsigned long long first = 0;
+        if (t == 0) first = atomicAdd(p.ctl, 1ull);
+        cur_tk = (int)(unsigned)__shfl_sync(kFull, (unsigned)first, 0);
+    }
+    StripRec cur = sq_load_rec(p.tab, cur_tk, p.nstrips);
     StripRec nxt;
     nxt.rows = 0;
     nxt.m = 0;
@@ -251,9 +256,13 @@ __global__ void __launch_bounds__(32) softdp_sq_fwd_kernel(const SqParams p) {
         const float* qstrip = ADJ ? p.Qin + cur.q_off : nullptr;
         if (p.trace && t == 0) p.trace[2 * cur_tk] = global_ns();
 
-        // the ticket after this one: the atomic's result is not needed before block 1
+        // The next ticket is taken late -- three blocks before this strip ends, its record read
+        // one block later: enough to hide the atomic, the record load and the first operand
+        // tiles, while a claimed strip never sits unstarted for more than ~50 steps (strips differ
+        // in length by 10x on ragged batches; a strip claimed at the start of a long one would
+        // hold up its whole dependency chain)
         unsigned long long pulled = 0;
-        if (t == 0) pulled = atomicAdd(p.ctl, 1ull);
+        const int b_pull = NBk > 3 ? NBk - 3 : 0, b_load = b_pull + 1;
         // the first 16 entries of the row above
         unsigned long long pfv = 0;
         if (has_up && t < 16 && t < m) pfv = ld_relaxed_gpu_u64(bin + t);
@@ -264,8 +273,9 @@ __global__ void __launch_bounds__(32) softdp_sq_fwd_kernel(const SqParams p) {
 
         for (int b = 0; b < NBk; ++b) {
             __syncwarp();
-            if (b == 1) {
-                nxt_tk = G + (int)(unsigned)__shfl_sync(kFull, (unsigned)pulled, 0);
+            if (b == b_pull && t == 0) pulled = atomicAdd(p.ctl, 1ull);
+            if (b == b_load) {
+                nxt_tk = (int)(unsigned)__shfl_sync(kFull, (unsigned)pulled, 0);
                 nxt = sq_load_rec(p.tab, nxt_tk, p.nstrips);
                 nxt_ready = true;
             }
@@ -478,9 +488,13 @@ __global__ void __launch_bounds__(32) softdp_sq_bwd_kernel(const SqParams p) {
                               st.m + 15 - kDiagRows * a, t, 0);
     };
 
-    const int G = (int)gridDim.x;
-    StripRec cur = sq_load_rec(p.tab, (int)blockIdx.x, p.nstrips);
-    int cur_tk = (int)blockIdx.x, nxt_tk = 0;
+    int cur_tk = 0, nxt_tk = 0;
+    {
+        unsigned long long first = 0;
+        if (t == 0) first = atomicAdd(p.ctl, 1ull);
+        cur_tk = (int)(unsigned)__shfl_sync(kFull, (unsigned)first, 0);
+    }
+    StripRec cur = sq_load_rec(p.tab, cur_tk, p.nstrips);
     StripRec nxt;
     nxt.rows = 0;
     nxt.m = 0;
@@ -503,8 +517,8 @@ __global__ void __launch_bounds__(32) softdp_sq_bwd_kernel(const SqParams p) {
         const float et = ADJ ? 0.f : p.Et[(long long)cur.pair * p.et_stride];
         if (p.trace && t == 0) p.trace[2 * cur_tk] = global_ns();
 
-        unsigned long long pulled = 0;
-        if (t == 0) pulled = atomicAdd(p.ctl, 1ull);
+        unsigned long long pulled = 0;                // next ticket: taken late, see the forward kernel
+        const int b_pull = NBk > 3 ? NBk - 3 : 0, b_load = b_pull + 1;
         // lane l < 16 fetches the entry lane 31 needs at step l: column m-1-l
         unsigned long long pfv = 0;
         if (has_below && t < 16 && m - 1 - t >= 0) pfv = ld_relaxed_gpu_u64(bin + (m - 1 - t));
@@ -515,8 +529,9 @@ __global__ void __launch_bounds__(32) softdp_sq_bwd_kernel(const SqParams p) {
 
         for (int b = 0; b < NBk; ++b) {
             __syncwarp();
-            if (b == 1) {
-                nxt_tk = G + (int)(unsigned)__shfl_sync(kFull, (unsigned)pulled, 0);
+            if (b == b_pull && t == 0) pulled = atomicAdd(p.ctl, 1ull);
+            if (b == b_load) {
+                nxt_tk = (int)(unsigned)__shfl_sync(kFull, (unsigned)pulled, 0);
                 nxt = sq_load_rec(p.tab, nxt_tk, p.nstrips);
                 nxt_ready = true;
             }

@@ -96,6 +96,7 @@ int b200dp_plan_build(const int32_t* xlen, const int32_t* ylen, int B, int N, in
     if (!info) return fail(-1, "b200dp_plan_build: info is null");
     if (!packed && (M % 4) != 0)
         return fail(-5, "b200dp_plan_build: the dense layout needs M % 4 == 0 (16-byte rows); use the packed layout");
+    constexpr long long kHopSteps = 56;          // steps by which a strip trails the strip it depends on
     std::vector<int> n(B), m(B), K(B);
     std::vector<long long> toff(B), qoff(B), boff(B);
     long long tcur = 0, qcur = 0, bcur = 0, cells = 0;
@@ -128,6 +129,28 @@ int b200dp_plan_build(const int32_t* xlen, const int32_t* ylen, int B, int N, in
         if (pair_off) pair_off[b] = toff[b];
         if (q_off) q_off[b] = qoff[b];
     }
+    // Grid size of each sweep.  work = warp-steps of all strips, chain = the longest dependency
+    // chain (strip k+1 trails strip k by kHopSteps).  With every warp productive a step slows
+    // down roughly linearly in the resident warps per SM, so when the batch is bound by its
+    // longest chain (ragged batches with a few long pairs) more resident warps only slow that
+    // chain: keep just enough warps that the throughput time matches the chain
+    // (measured on B200, BASELINE configs[4]: 8 warps per SM 0.345 ms forward, 13 per SM 0.426 ms).
+    long long work = 0, chain = 1;
+    for (int b = 0; b < B; ++b) {
+        if (K[b] == 0) continue;
+        work += (long long)K[b] * (m[b] + 31);
+        chain = std::max(chain, (long long)(K[b] - 1) * kHopSteps + m[b] + 31);
+    }
+    auto pick_grid = [&](int resident) {
+        if (resident < 1) resident = 148 * 12;
+        if (nstrips <= resident) return std::max(nstrips, 1);
+        long long want = (work + chain / 2) / chain;                    // warps at which throughput time = chain time
+        const long long floor_ = (long long)resident * 45 / 100;        // (below that the step time no longer improves)
+        if (want < floor_) want = floor_;
+        return (int)std::min<long long>(want, resident);
+    };
+    info->grid_fwd = pick_grid(warps_fwd);
+    info->grid_bwd = pick_grid(warps_bwd);
     info->nstrips = nstrips;
     info->max_m = maxm;
     info->q_floats = qcur + (long long)kDiagRows * kStepFloats;     // tile reads may run past the last strip
@@ -145,7 +168,6 @@ int b200dp_plan_build(const int32_t* xlen, const int32_t* ylen, int B, int N, in
     // so every strip comes after the strip it depends on, long pairs are pipelined from the
     // first moment with other pairs' strips filling the gaps, and a warp seldom takes a strip
     // whose predecessor is not yet far enough ahead.
-    constexpr long long kHopSteps = 56;
     StripRec* ft = static_cast<StripRec*>(fwd_tab);
     StripRec* bt = static_cast<StripRec*>(bwd_tab);
     auto fill = [&](StripRec& s, int b, int k, bool fwd) {
@@ -207,8 +229,8 @@ int b200dp_plan_build(const int32_t* xlen, const int32_t* ylen, int B, int N, in
             }
         }
     };
-    schedule(warps_fwd, ft, true);
-    schedule(warps_bwd, bt, false);
+    schedule(info->grid_fwd, ft, true);
+    schedule(info->grid_bwd, bt, false);
     return 0;
 }
 

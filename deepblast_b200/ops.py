@@ -256,6 +256,13 @@ SQ_RING_SHIFT = 24
 CTAS_SHIFT = 8
 
 
+def _sq_flags(plan, flags, fwd):
+    """The plan's grid size unless the caller forces one."""
+    if (flags >> CTAS_SHIFT) & 0xFFFF:
+        return flags
+    return flags | ((plan.grid_fwd if fwd else plan.grid_bwd) << CTAS_SHIFT)
+
+
 def _sq_ws(plan, t):
     from . import plan as _plan
     stream = _stream(t)
@@ -295,6 +302,10 @@ def route_plan(theta, xlen=None, ylen=None):
             sms = _sm_count[theta.device.index] = torch.cuda.get_device_properties(theta.device).multi_processor_count
         if B >= 4 * sms and N >= 32 and M >= 64 and M % 32 == 0:
             return None                      # large equal-size batch: the chained kernels
+        if B > 64 and N < 512:
+            return None                      # many short pairs, too few for chaining: the hand-off kernels
+                                             # (measured on B200: 256 x 256^2 104 against 92 G cell-updates/s;
+                                             # 32 x 1024^2 37 against 64, 512 x 1024^2 160 against 177)
     return _plan.get_plan(B, N, M, xlen, ylen, False, theta.device)
 
 
@@ -311,7 +322,7 @@ def sq_forward(plan, theta, A, mode="nw", need_q=True, flags=0):
         Vt = alloc(plan.B, dtype=torch.float32, device=theta.device)
         ws, epoch, stream = _sq_ws(plan, theta)
         rc = _lib.lib().b200dp_sq_fwd(_ptr(plan.fwd_tab), plan.nstrips, _ptr(ws), epoch, _ptr(theta), _ptr(A),
-                                      _ptr(Q), _ptr(Vt), MODES[mode], flags, stream)
+                                      _ptr(Q), _ptr(Vt), MODES[mode], _sq_flags(plan, flags, True), stream)
         _lib.check(rc, "b200dp_sq_fwd")
     return Vt, Q
 
@@ -335,7 +346,8 @@ def sq_backward(plan, Et, Q, mode="nw", flags=0):
         E = _sq_out_like(plan, Q)
         ws, epoch, stream = _sq_ws(plan, Q)
         rc = _lib.lib().b200dp_sq_bwd(_ptr(plan.bwd_tab), plan.nstrips, _ptr(ws), epoch, _ptr(Et),
-                                      Et.stride(0) if plan.B > 0 else 0, _ptr(Q), _ptr(E), MODES[mode], flags, stream)
+                                      Et.stride(0) if plan.B > 0 else 0, _ptr(Q), _ptr(E), MODES[mode],
+                                      _sq_flags(plan, flags, False), stream)
         _lib.check(rc, "b200dp_sq_bwd")
     return E
 
@@ -357,7 +369,7 @@ def sq_adjoint_forward(plan, Q, Zt, ZA=None, E=None, flags=0):
         Vtd = alloc(plan.B, dtype=torch.float32, device=Q.device)
         ws, epoch, stream = _sq_ws(plan, Q)
         rc = _lib.lib().b200dp_sq_adj_fwd(_ptr(plan.fwd_tab), plan.nstrips, _ptr(ws), epoch, _ptr(Q), _ptr(Zt),
-                                          _ptr(ZA), _ptr(E), _ptr(Vtd), _ptr(QdE), flags, stream)
+                                          _ptr(ZA), _ptr(E), _ptr(Vtd), _ptr(QdE), _sq_flags(plan, flags, True), stream)
         _lib.check(rc, "b200dp_sq_adj_fwd")
     return Vtd, QdE
 
@@ -369,7 +381,7 @@ def sq_adjoint_backward(plan, Q, QdE, flags=0):
         Ed = _sq_out_like(plan, Q)
         ws, epoch, stream = _sq_ws(plan, Q)
         rc = _lib.lib().b200dp_sq_adj_bwd(_ptr(plan.bwd_tab), plan.nstrips, _ptr(ws), epoch, _ptr(Q), _ptr(QdE),
-                                          _ptr(Ed), flags, stream)
+                                          _ptr(Ed), _sq_flags(plan, flags, False), stream)
         _lib.check(rc, "b200dp_sq_adj_bwd")
     return Ed
 

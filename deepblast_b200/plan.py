@@ -28,7 +28,7 @@ from . import _lib
 class _PlanInfo(ctypes.Structure):
     _fields_ = [("nstrips", ctypes.c_int), ("max_m", ctypes.c_int), ("q_floats", ctypes.c_longlong),
                 ("bnd_words", ctypes.c_longlong), ("packed_floats", ctypes.c_longlong),
-                ("cells", ctypes.c_longlong)]
+                ("cells", ctypes.c_longlong), ("grid_fwd", ctypes.c_int), ("grid_bwd", ctypes.c_int)]
 
 
 def _lens_host(x, B, name):
@@ -82,6 +82,7 @@ class Plan:
         self.q_floats, self.bnd_words = info.q_floats, info.bnd_words
         self.packed_floats, self.cells, self.max_m = info.packed_floats, info.cells, info.max_m
         self.ws_bytes = L.b200dp_sq_workspace_bytes(info.bnd_words)
+        self.grid_fwd, self.grid_bwd = info.grid_fwd, info.grid_bwd
         self.xlen = np.full(B, N, np.int32) if xl is None else np.clip(xl, 0, N)
         self.ylen = np.full(B, M, np.int32) if yl is None else np.clip(yl, 0, M)
         empty = (self.xlen == 0) | (self.ylen == 0)

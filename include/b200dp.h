@@ -195,6 +195,8 @@ typedef struct b200dp_plan_info {
     long long bnd_words;       /* 8-byte words of boundary scratch (b200dp_sq_workspace_bytes) */
     long long packed_floats;   /* floats of a theta / A / E buffer in this layout */
     long long cells;           /* sum of n_b * m_b */
+    int grid_fwd, grid_bwd;    /* warps (CTAs) to launch the forward- / backward-direction sweeps with
+                                  (pass through the B200DP_CTAS_SHIFT field of flags) */
 } b200dp_plan_info;
 
 int b200dp_plan_build(const int32_t* xlen, const int32_t* ylen, int B, int N, int M, int packed,
