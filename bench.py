@@ -2,7 +2,7 @@
 """bench.py -- DP cell-updates/s (forward + backward) of the batched soft-DP alignment
 path on B200, next to the CPU oracle port timed on the same box.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--no-extras]
     python bench.py --impl reference ...      # CPU arm (oracle port, all host threads)
     torchrun --nproc-per-node N ... bench.py --gpus N ...
 
@@ -12,6 +12,16 @@ A step = one pass of the hot path over one batch: NeedlemanWunschFunction.apply
 the reference's autograd API.  Metric and byte accounting: SURVEY.md section 8(d):
 36 algorithmic bytes per cell-update (fwd: theta 4 + A 4 read, Q 12 written;
 bwd: Q 12 read, E 4 written).
+
+The JSON line's headline (`value`, `roofline`, `e2e`, `cpu_baseline`) is the workload named
+by --workload (default: BASELINE configs[1], C2); unless --no-extras the same line carries
+`workloads`: every other BASELINE config (c3, c4 slice, c5 packed ragged), a small batch of
+long pairs and two training-shaped steps, each timed the same way under the same clock.
+
+The forward and the backward of a step are captured once in two CUDA graphs (through the public
+autograd API, static input buffers) and replayed: the timed region holds K x {fwd graph, bwd
+graph} with CUDA events between them, so the per-kernel times are device times and the host
+only enqueues two graph launches per step.  `eager` reports the same K steps issued call by call.
 """
 import argparse
 import json
@@ -35,7 +45,9 @@ WORKLOADS = {
     "c2": ("nw", 1024, 256, 256, "BASELINE configs[1]: batch=1024 pairs 256x256, NW forward+backward fp32"),
     "c3": ("sw", 1024, 256, 256, "BASELINE configs[2]: batch=1024 pairs 256x256, Smith-Waterman soft-DP"),
     "c4": ("nw", 1024, 512, 512, "BASELINE configs[3]: 8192 pairs 512x512 batch-sharded 8 ways = 1024 pairs/GPU"),
-    "c5": ("nw", 1024, 1024, 1024, "BASELINE configs[4]: variable lengths 64..1024 (Zipf over 16 buckets), 1024 pairs/GPU"),
+    "c5": ("nw", 1024, 1024, 1024, "BASELINE configs[4]: variable lengths 64..1024 (Zipf over 16 buckets), 1024 pairs/GPU, "
+                                   "PACKED layout (no padding to the longest pair)"),
+    "b32": ("nw", 32, 1024, 1024, "small batch of long pairs: 32 pairs 1024x1024 (trainer.py:375 batch size, max_len 1024)"),
 }
 
 
@@ -45,16 +57,6 @@ def peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
-
-
-def kernel_name(dom, B, N, M, varlen):
-    """Which kernel b200dp_fwd / b200dp_bwd dispatch to for this workload (softdp_api.cu):
-    the chained single-warp kernels for large batches of equal-size lattices, the hand-off
-    kernels otherwise."""
-    import torch
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
-    chained = (not varlen) and B >= 4 * sms and N >= 32 and M >= 64 and M % (16 if dom == "fwd" else 32) == 0
-    return f"softdp_{dom}{3 if chained else 2}_kernel"
 
 
 def zipf_lengths(B, rng):
@@ -205,8 +207,10 @@ def reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "mode": mode, "N": N, "M": M,
-                   "note": "reference is Python+Numba (not compilable to oracle/_ref); this arm times the C oracle "
+        "config": {"workload": desc, "mode": mode, "pairs_per_gpu": Bg, "N": N, "M": M,
+                   "global_pairs": Bg * args.gpus,
+                   "parallelism": f"batch-sliced x{args.gpus}, no DP collective",
+                   "note": "the reference is Python+Numba (not compilable to oracle/_ref); this arm times the C oracle "
                            "port of deepblast/nw.py with OpenMP over pairs on a bounded sample per step"},
         "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port",
                          "sample": sample},
@@ -217,6 +221,348 @@ def reference_arm(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------
+class Ctx:
+    pass
+
+
+def make_workload(cx, name, pairs_override=0):
+    """Synthetic inputs of one workload on this rank: theta, A (dense or packed), plan, cells."""
+    import torch
+    from deepblast_b200 import plan as P
+    mode, Bg, N, M, desc = WORKLOADS[name]
+    if pairs_override:
+        Bg = pairs_override
+    w = Ctx()
+    w.name, w.mode, w.N, w.M, w.desc = name, mode, N, M, desc
+    gen = torch.Generator(device=cx.dev).manual_seed(2 + cx.rank)
+    w.plan = None
+    w.stats = {}
+    if name == "c5":
+        from deepblast_b200.sharding import lpt_assign, packing_stats
+        xl_all, yl_all = zipf_lengths(Bg * cx.world, np.random.default_rng(0))
+        asg = lpt_assign(xl_all * yl_all, cx.world)
+        w.stats = packing_stats(xl_all, yl_all, asg)
+        mine = asg[cx.rank]
+        w.xl, w.yl = xl_all[mine].astype(np.int32), yl_all[mine].astype(np.int32)
+        Bg = len(mine)
+        w.plan = P.get_plan(Bg, int(w.xl.max()), int(w.yl.max()), w.xl, w.yl, True, cx.dev)
+        w.stats["padded_cells_if_dense"] = int(Bg * 1024 * 1024)
+        w.stats["packed_floats"] = int(w.plan.packed_floats)
+        shape = (w.plan.packed_floats,)
+        w.cells = int(w.plan.cells)
+    else:
+        w.xl = w.yl = None
+        shape = (Bg, N, M)
+        w.cells = Bg * (N - 1) * (M - 1) if mode == "sw" else Bg * N * M
+    w.B = Bg
+    w.theta = torch.rand(shape, generator=gen, device=cx.dev).requires_grad_()
+    w.A = -torch.rand(shape, generator=gen, device=cx.dev)
+    return w
+
+
+def step_fns(cx, w):
+    """(forward, backward) closures through the public autograd API."""
+    import torch
+    from deepblast_b200.nw_cuda import NeedlemanWunschFunction
+    from deepblast_b200.sw_cuda import SmithWatermanFunction
+    Fn = NeedlemanWunschFunction if w.mode == "nw" else SmithWatermanFunction
+    st = {}
+
+    def fwd():
+        if w.plan is None:
+            st["Vt"] = Fn.apply(w.theta, w.A, 'softmax')
+        else:
+            st["Vt"] = Fn.apply(w.theta, w.A, 'softmax', None, None, w.plan)
+
+    def bwd():
+        st["g"], = torch.autograd.grad(st["Vt"].sum(), w.theta)
+    return fwd, bwd, st
+
+
+def time_workload(cx, w, steps, warmup, use_graph=True):
+    """W warm-up steps, then exactly `steps` timed steps bracketed by barrier + synchronize; CUDA
+    events between the forward and the backward of every step.  Returns a dict of timings."""
+    import torch
+    import torch.distributed as dist
+    fwd, bwd, st = step_fns(cx, w)
+
+    def sync_all():
+        if cx.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    res = {}
+    # ---- eager: call by call (also the warm-up of every lazy initialisation) ------------------
+    for it in range(max(warmup, 3)):
+        fwd(); bwd()
+        if it == 0:
+            sync_all()
+    sync_all()
+    n_e = max(3, min(steps, 10))
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_e)]
+    t0 = time.perf_counter()
+    for it in range(n_e):
+        ev[it][0].record(); fwd(); ev[it][1].record(); bwd(); ev[it][2].record()
+    host_eager = (time.perf_counter() - t0) * 1e3 / n_e
+    torch.cuda.synchronize()
+    res["eager"] = {"ms_per_step": ev[0][0].elapsed_time(ev[-1][2]) / n_e,
+                    "host_enqueue_ms_per_step": host_eager, "steps": n_e}
+    # ---- graphs: forward and backward captured once, replayed ------------------------------------
+    run_f, run_b, graphed = fwd, bwd, False
+    for attempt in range(2 if use_graph else 0):
+        try:
+            # (the whole benchmark runs on cx.side, a non-default stream: a leaf first used on the
+            # legacy default stream would make its backward synchronise with that stream, which
+            # a capture cannot express)
+            side = torch.cuda.current_stream(cx.dev)
+            st.clear()
+            for _ in range(3):
+                fwd(); bwd()
+            torch.cuda.synchronize()
+            gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gf, stream=side):
+                fwd()
+            with torch.cuda.graph(gb, pool=gf.pool(), stream=side):
+                bwd()
+            run_f, run_b, graphed = gf.replay, gb.replay, True
+            res.pop("graph_error", None)
+            break
+        except Exception as e:                           # capture not possible here: stay eager, say so
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            res["graph_error"] = f"attempt {attempt}: {type(e).__name__}: {str(e)[:160]}"
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+    for _ in range(max(warmup, 3)):
+        run_f(); run_b()
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    sync_all()
+    host_t0 = time.perf_counter()
+    ev0.record()
+    for it in range(steps):
+        kev[it][0].record(); run_f(); kev[it][1].record(); run_b(); kev[it][2].record()
+    ev1.record()
+    host_ms = (time.perf_counter() - host_t0) * 1e3 / steps
+    torch.cuda.synchronize()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=cx.dev)
+    cells = torch.tensor([float(w.cells)], dtype=torch.float64, device=cx.dev)
+    if cx.world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cells, op=dist.ReduceOp.SUM)
+    res.update({
+        "ms_total": float(t.item()), "total_cells": float(cells.item()), "graphed": graphed,
+        "fwd_ms": float(np.mean([k[0].elapsed_time(k[1]) for k in kev])),
+        "bwd_ms": float(np.mean([k[1].elapsed_time(k[2]) for k in kev])),
+        "host_enqueue_ms_per_step": host_ms,
+        "step_ms_median": float(np.median([k[0].elapsed_time(k[2]) for k in kev])),
+        "step_ms_max": float(np.max([k[0].elapsed_time(k[2]) for k in kev])),
+        "step_ms_first3": [round(k[0].elapsed_time(k[2]), 4) for k in kev[:3]],
+    })
+    # keep the captured graphs (and their pool) alive until the numbers are out
+    res["_keep"] = (run_f, run_b, st)
+    return res
+
+
+def kernel_names(cx, w):
+    """Which kernels the dispatch picks for this workload (deepblast_b200/ops.py route_plan,
+    _functions.py): forward, backward."""
+    sms = cx.sms
+    if w.plan is not None:
+        return "softdp_sq_fwd_kernel", "softdp_sq_bwd_kernel"
+    chained = w.B >= 4 * sms and w.N >= 32 and w.M >= 64 and w.M % 32 == 0
+    if chained:
+        return "softdp_fwd3_kernel", "softdp_sq_bwd_kernel"
+    if w.B <= 64 or w.N >= 512:
+        return "softdp_sq_fwd_kernel", "softdp_sq_bwd_kernel"
+    return "softdp_fwd2_kernel", "softdp_bwd2_kernel"
+
+
+def roofline(cx, w, r, traffic_tab):
+    peak, peak_src = peaks()
+    fwd_gbs = w.cells * BYTES_FWD / (r["fwd_ms"] * 1e-3) / 1e9
+    bwd_gbs = w.cells * BYTES_BWD / (r["bwd_ms"] * 1e-3) / 1e9
+    dom = "fwd" if r["fwd_ms"] >= r["bwd_ms"] else "bwd"
+    ach = fwd_gbs if dom == "fwd" else bwd_gbs
+    kf, kb = kernel_names(cx, w)
+    traffic = traffic_tab.get(f"{w.name}_{dom}")
+    dom_ms = r["fwd_ms"] if dom == "fwd" else r["bwd_ms"]
+    return {"bound": "hbm", "kernel": kf if dom == "fwd" else kb, "achieved": ach, "peak": peak, "unit": "GB/s",
+            "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+            # measured DRAM bytes of that launch (ncu, profiles/traffic.json) over the live duration: the
+            # kernels store two of the three Q states, so they move fewer bytes than the 36 B/cell contract
+            "traffic_GBps": (traffic / (dom_ms * 1e-3) / 1e9) if traffic else None,
+            "traffic_frac": (traffic / (dom_ms * 1e-3) / 1e9 / peak) if traffic else None,
+            "algorithmic_bytes_per_cell": BYTES_FWD if dom == "fwd" else BYTES_BWD,
+            "fwd": {"kernel": kf, "ms": r["fwd_ms"], "GBps": fwd_gbs, "frac": fwd_gbs / peak},
+            "bwd": {"kernel": kb, "ms": r["bwd_ms"], "GBps": bwd_gbs, "frac": bwd_gbs / peak}}
+
+
+def host_ceiling(cx, h2d_bytes, d2h_bytes, reps=5):
+    """What the box's host link allows for one step's copies alone: plain pinned cudaMemcpyAsync of
+    the same byte counts, uploads and downloads on two streams at once, every rank at the same
+    time (barrier first).  ms per step on this rank (max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    hb = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, pin_memory=True)
+    hd = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, pin_memory=True)
+    db = torch.empty(max(h2d_bytes, 1), dtype=torch.uint8, device=cx.dev)
+    dd = torch.empty(max(d2h_bytes, 1), dtype=torch.uint8, device=cx.dev)
+    s1, s2 = torch.cuda.Stream(device=cx.dev), torch.cuda.Stream(device=cx.dev)
+
+    def once():
+        with torch.cuda.stream(s1):
+            db.copy_(hb, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hd.copy_(dd, non_blocking=True)
+    once()
+    torch.cuda.synchronize()
+    if cx.world > 1:
+        dist.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    s1.wait_event(e0); s2.wait_event(e0)
+    for _ in range(reps):
+        once()
+    e1.record(s1); e2.record(s2)
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(e1), e0.elapsed_time(e2)) / reps
+    t = torch.tensor([ms], dtype=torch.float64, device=cx.dev)
+    if cx.world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def e2e_dense(cx, w, nst):
+    """Host buffers in, host results out, every step, through Decoder.decode_host -> C ABI
+    b200dp_decode_host (chunked upload | fwd+bwd | download on three streams)."""
+    import torch
+    import torch.distributed as dist
+    from deepblast_b200 import ops
+    B, N, M = w.B, w.N, w.M
+    h_theta = torch.empty((B, N, M), dtype=torch.float32, pin_memory=True).copy_(w.theta.detach().cpu())
+    h_A = torch.empty((B, N, M), dtype=torch.float32, pin_memory=True).copy_(w.A.cpu())
+    h_Vt = torch.empty(B, dtype=torch.float32, pin_memory=True)
+    h_E = torch.empty((B, N + 2, M + 2), dtype=torch.float32, pin_memory=True)
+
+    def step():
+        ops.decode_host_async(h_theta, h_A, w.mode, out=(h_Vt, h_E), device=cx.dev)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if cx.world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(nst):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=cx.dev)
+    if cx.world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    h2d, d2h = int(2 * B * N * M * 4), int(B * (N + 2) * (M + 2) * 4 + B * 4)
+    return float(te.item()) / nst, h2d, d2h, (
+        "pinned host theta/A -> b200dp_decode_host (chunked H2D | fwd+bwd | D2H pipeline, 3 streams) -> "
+        "pinned host Vt and padded E (dVt/dtheta = E[:,1:-1,1:-1]), per rank")
+
+
+def e2e_packed(cx, w, nst):
+    """Ragged batch, host buffers in the PACKED layout: only the useful cells cross PCIe.  The
+    batch is cut into chunks of pairs; upload, sweeps and download of consecutive chunks overlap
+    (deepblast_b200.packed.PackedHostDecoder)."""
+    import torch
+    import torch.distributed as dist
+    from deepblast_b200.packed import PackedHostDecoder
+    dec = PackedHostDecoder(w.xl, w.yl, w.mode, device=cx.dev)
+    h_theta = torch.empty(dec.packed_floats, dtype=torch.float32, pin_memory=True).uniform_()
+    h_A = torch.empty(dec.packed_floats, dtype=torch.float32, pin_memory=True).uniform_().neg_()
+    for _ in range(2):
+        dec.decode(h_theta, h_A)
+    torch.cuda.synchronize()
+    if cx.world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(nst):
+        dec.decode(h_theta, h_A)
+    e1.record()
+    torch.cuda.synchronize()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=cx.dev)
+    if cx.world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    h2d, d2h = int(2 * dec.packed_floats * 4), int(dec.packed_floats * 4 + w.B * 4)
+    return float(te.item()) / nst, h2d, d2h, (
+        f"pinned host PACKED theta/A -> {dec.nchunks} chunks: H2D | strip-queue fwd+bwd | D2H on three streams -> "
+        "pinned host Vt and packed dVt/dtheta, per rank")
+
+
+def train_step_bench(cx, B, N, M, steps):
+    """Training-shaped step (trainer.py:154-188): decode (forward + backward, create_graph) ->
+    MatrixCrossEntropy -> loss.backward() (the adjoint pair).  Eager, and replayed from one CUDA graph."""
+    import torch
+    from deepblast_b200.nw_cuda import NeedlemanWunschDecoder
+    from deepblast_b200.losses import MatrixCrossEntropy
+    g = torch.Generator(device=cx.dev).manual_seed(5)
+    theta = torch.rand(B, N, M, generator=g, device=cx.dev).requires_grad_()
+    A = (-torch.rand(B, N, M, generator=g, device=cx.dev)).requires_grad_()
+    Ytrue = (torch.rand(B, N, M, generator=g, device=cx.dev) < 0.01).float()
+    G = torch.ones(B, N, M, device=cx.dev)
+    xl = torch.full((B,), N, dtype=torch.int32, device=cx.dev)
+    yl = torch.full((B,), M, dtype=torch.int32, device=cx.dev)
+    dec, crit = NeedlemanWunschDecoder('softmax'), MatrixCrossEntropy()
+    st = {}
+
+    def step():
+        theta.grad = None
+        aln = dec.decode(theta, A)
+        loss = crit(Ytrue, aln, xl, yl, G)
+        loss.backward()
+        st["loss"] = loss
+
+    def timeit(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        host = (time.perf_counter() - t0) * 1e3 / n
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, host
+    out = {"B": B, "N": N, "M": M, "cells": B * N * M}
+    ms, host = timeit(step, steps)
+    out["eager_ms"], out["eager_host_ms"] = ms, host
+    try:
+        side = torch.cuda.current_stream(cx.dev)
+        st.clear()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        theta.grad = None
+        with torch.cuda.graph(gr, stream=side):
+            aln = dec.decode(theta, A)
+            loss = crit(Ytrue, aln, xl, yl, G)
+            gth, = torch.autograd.grad(loss, theta)
+        ms, host = timeit(gr.replay, steps)
+        out["graph_ms"], out["graph_host_ms"] = ms, host
+        out["_keep"] = (gr, gth)
+    except Exception as e:
+        out["graph_error"] = f"{type(e).__name__}: {str(e)[:160]}"
+        torch.cuda.synchronize()
+    best = out.get("graph_ms", out["eager_ms"])
+    out["cell_updates_per_s_4_sweeps"] = B * N * M / (best * 1e-3)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,9 +571,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs-per-gpu", type=int, default=0)
-    ap.add_argument("--cpu-seconds", type=float, default=18.0)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline workload")
+    ap.add_argument("--no-graph", action="store_true", help="time eager calls only")
     ap.add_argument("--no-bind", action="store_true", help="do not bind the process to the GPU-local CPU cores")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -235,216 +583,137 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from deepblast_b200 import ops
-    from deepblast_b200.nw_cuda import NeedlemanWunschFunction
-    from deepblast_b200.sw_cuda import SmithWatermanFunction
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: deepblast_b200 has no CPU path")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
+    cx = Ctx()
+    cx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    cx.dev = torch.device("cuda", local)
+    cx.sms = torch.cuda.get_device_properties(cx.dev).multi_processor_count
     affinity = bind_to_gpu_numa_node(local) if not args.no_bind else "unbound (--no-bind)"
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if world != args.gpus and rank == 0:
-        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    if cx.world > 1:
+        dist.init_process_group("nccl", device_id=cx.dev)
+    if cx.world != args.gpus and cx.rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={cx.world}", file=sys.stderr)
+    cx.side = torch.cuda.Stream(device=cx.dev)
+    torch.cuda.set_stream(cx.side)                     # everything below: one non-default stream
+    traffic_tab = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic_tab = json.load(f)
+    steps, warmup = args.steps, max(args.warmup, 3)
 
-    mode, Bg, N, M, desc = WORKLOADS[args.workload]
-    if args.pairs_per_gpu:
-        Bg = args.pairs_per_gpu
-    Fn = NeedlemanWunschFunction if mode == "nw" else SmithWatermanFunction
-    gen = torch.Generator(device=dev).manual_seed(2 + rank)
-    theta = torch.rand(Bg, N, M, generator=gen, device=dev)
-    A = -torch.rand(Bg, N, M, generator=gen, device=dev)
-    theta.requires_grad_()
-    xlen = ylen = None
-    stats = {}
-    if args.workload == "c5":
-        from deepblast_b200.sharding import lpt_assign, packing_stats
-        xl_all, yl_all = zipf_lengths(Bg * world, np.random.default_rng(0))
-        asg = lpt_assign(xl_all * yl_all, world)
-        stats = packing_stats(xl_all, yl_all, asg)
-        mine = asg[rank][:Bg] if len(asg[rank]) >= Bg else asg[rank]
-        Bg = len(mine)
-        theta = theta.detach()[:Bg].requires_grad_()
-        A = A[:Bg]
-        xlen = torch.tensor(xl_all[mine], dtype=torch.int32, device=dev)
-        ylen = torch.tensor(yl_all[mine], dtype=torch.int32, device=dev)
-        cells_local = int((xl_all[mine].astype(np.int64) * yl_all[mine]).sum())
-    elif mode == "sw":
-        cells_local = Bg * (N - 1) * (M - 1)
-    else:
-        cells_local = Bg * N * M
-
-    def step():
-        if xlen is None:
-            Vt = Fn.apply(theta, A, 'softmax')
-        else:
-            Vt = Fn.apply(theta, A, 'softmax', xlen, ylen)
-        g, = torch.autograd.grad(Vt.sum(), theta)
-        return Vt, g
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # warm-up: W untimed steps, with the rendezvous barrier exercised in between so that
-    # every lazy initialisation (NCCL communicator, allocator pools, autograd worker
-    # threads) happens before the timed region.  The results of a step stay referenced
-    # while the next one runs, exactly as in the timed loop below, so that the caching
-    # allocator already owns every block the timed steps will ask for.
-    keep = None
-    for it in range(max(args.warmup, 3)):
-        keep = step()
-        if it == 0:
-            sync_all()
-    sync_all()
-
+    # ---- headline ---------------------------------------------------------------------------------
+    w = make_workload(cx, args.workload, args.pairs_per_gpu)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if cx.rank == 0:
         sampler.start()
         time.sleep(0.3)
-    # ---- timed region: exactly K steps, CUDA events on the launching stream -------
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    sync_all()
-    # keep the device busy for ~2 ms (untimed) while the host enqueues the first steps, so
-    # that the K timed steps run back to back on the GPU instead of waiting for Python
-    torch.cuda._sleep(int(4e6))
-    host_t0 = time.perf_counter()
-    ev0.record()
-    for it in range(args.steps):
-        kev[it][0].record()
-        if xlen is None:
-            Vt = Fn.apply(theta, A, 'softmax')
-        else:
-            Vt = Fn.apply(theta, A, 'softmax', xlen, ylen)
-        kev[it][1].record()
-        g, = torch.autograd.grad(Vt.sum(), theta)
-        kev[it][2].record()
-        keep = (Vt, g)
-    ev1.record()
-    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps     # enqueue time, GPU not waited for
-    torch.cuda.synchronize()
-    sync_all()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    cells = torch.tensor([float(cells_local)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cells, op=dist.ReduceOp.SUM)
-    ms = float(t.item())
-    total_cells = float(cells.item())
-    value = total_cells * args.steps / (ms * 1e-3)
-    fwd_ms = float(np.mean([k[0].elapsed_time(k[1]) for k in kev]))
-    bwd_ms = float(np.mean([k[1].elapsed_time(k[2]) for k in kev]))
+    r = time_workload(cx, w, steps, warmup, use_graph=not args.no_graph)
+    clocks = sampler.stop() if cx.rank == 0 else None
+    value = r["total_cells"] * steps / (r["ms_total"] * 1e-3)
 
-    # ---- end to end: host buffers in, host results out, every step --------------------
-    e2e = None
-    if not args.no_e2e:
-        # the reference-facing call for a caller whose theta / A live in HOST memory:
-        # Decoder.decode_host -> C ABI b200dp_decode_host (pinned host buffers in, pinned host
-        # Vt and padded E out; chunked upload / fwd / bwd / download pipeline inside).
-        h_theta = torch.empty((Bg, N, M), dtype=torch.float32, pin_memory=True).copy_(theta.detach().cpu())
-        h_A = torch.empty((Bg, N, M), dtype=torch.float32, pin_memory=True).copy_(A.cpu())
-        h_Vt = torch.empty(Bg, dtype=torch.float32, pin_memory=True)
-        h_E = torch.empty((Bg, N + 2, M + 2), dtype=torch.float32, pin_memory=True)
-        if xlen is None:
-            def e2e_step():
-                ops.decode_host_async(h_theta, h_A, mode, out=(h_Vt, h_E), device=dev)
-            d2h = int(Bg * (N + 2) * (M + 2) * 4 + Bg * 4)
-            note = ("pinned host theta/A -> b200dp_decode_host (chunked H2D | fwd+bwd | D2H pipeline, 3 streams) -> "
-                    "pinned host Vt and padded E (dVt/dtheta = E[:,1:-1,1:-1]), per rank")
-        else:
-            h_g = torch.empty((Bg, N, M), dtype=torch.float32, pin_memory=True)
+    def e2e_of(wk, nst):
+        ms, h2d, d2h, note = (e2e_packed if wk.plan is not None and wk.plan.packed else e2e_dense)(cx, wk, nst)
+        cells = torch.tensor([float(wk.cells)], dtype=torch.float64, device=cx.dev)
+        if cx.world > 1:
+            dist.all_reduce(cells, op=dist.ReduceOp.SUM)
+        ceil_ms = host_ceiling(cx, h2d, d2h)
+        return {"value": float(cells.item()) / (ms * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms, "steps": nst, "host_affinity": affinity,
+                # the same bytes as plain pinned copies, both directions at once, all ranks together
+                "host_ceiling_ms_per_step": ceil_ms, "frac_of_host_ceiling": ceil_ms / ms, "note": note}
 
-            def e2e_step():
-                th = h_theta.to(dev, non_blocking=True).requires_grad_()
-                a = h_A.to(dev, non_blocking=True)
-                Vt = Fn.apply(th, a, 'softmax', xlen, ylen)
-                gg, = torch.autograd.grad(Vt.sum(), th)
-                h_Vt.copy_(Vt.detach(), non_blocking=True)
-                h_g.copy_(gg, non_blocking=True)
-            d2h = int(Bg * N * M * 4 + Bg * 4)
-            note = "pinned host theta/A -> H2D -> Function fwd + backward (per-pair lengths) -> Vt and dVt/dtheta D2H, per rank"
+    e2e = None if args.no_e2e else e2e_of(w, max(3, min(steps, 10)))
 
-        for _ in range(2):
-            e2e_step()
-        sync_all()
-        nst = max(3, min(args.steps, 10))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(nst):
-            e2e_step()
-        e1.record()
-        torch.cuda.synchronize()
-        sync_all()
-        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_cells * nst / (float(te.item()) * 1e-3), "unit": "cell-updates/s",
-               "h2d_bytes_per_step": int(2 * Bg * N * M * 4), "d2h_bytes_per_step": d2h,
-               "ms_per_step": float(te.item()) / nst, "steps": nst, "host_affinity": affinity, "note": note}
-
-    if rank == 0:
-        peak, peak_src = peaks()
-        n_cells_launch = cells_local
-        fwd_gbs = n_cells_launch * BYTES_FWD / (fwd_ms * 1e-3) / 1e9
-        bwd_gbs = n_cells_launch * BYTES_BWD / (bwd_ms * 1e-3) / 1e9
-        dom = "fwd" if fwd_ms >= bwd_ms else "bwd"
-        ach = fwd_gbs if dom == "fwd" else bwd_gbs
-        step_gbs = n_cells_launch * (BYTES_FWD + BYTES_BWD) / ((ms / args.steps) * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                traffic = json.load(f).get(f"{args.workload}_{dom}")
+    line = None
+    if cx.rank == 0:
+        rf = roofline(cx, w, r, traffic_tab)
+        step_gbs = w.cells * (BYTES_FWD + BYTES_BWD) / ((r["ms_total"] / steps) * 1e-3) / 1e9
+        rf["step"] = {"GBps_at_36B_per_cell": step_gbs, "frac": step_gbs / rf["peak"]}
         line = {
-            "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "metric": METRIC, "value": value, "unit": "cell-updates/s", "n_gpus": cx.world,
+            "steps": steps, "warmup": warmup, "ms_per_step": r["ms_total"] / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": desc, "mode": mode, "pairs_per_gpu": Bg, "N": N, "M": M,
-                       "global_pairs": Bg * world, "parallelism": f"batch-sliced x{world}, no DP collective",
+            "config": {"workload": w.desc, "mode": w.mode, "pairs_per_gpu": w.B, "N": w.N, "M": w.M,
+                       "global_pairs": w.B * cx.world, "parallelism": f"batch-sliced x{cx.world}, no DP collective",
                        "l2": "inputs (theta+A %.0f MB, Q %.0f MB per GPU) exceed the 126 MB L2; no flush needed"
-                             % (2 * Bg * N * M * 4 / 1e6, Bg * (N + 2) * (M + 2) * 12 / 1e6),
-                       **({"packing": stats} if stats else {})},
-            "roofline": {"bound": "hbm", "kernel": kernel_name(dom, Bg, N, M, xlen is not None), "achieved": ach,
-                         "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                         # measured DRAM bytes of that launch (ncu, profiles/traffic.json) over the live
-                         # duration: the kernels store two of the three Q states, so they move fewer bytes
-                         # than the 36 B/cell contract `achieved` is quoted on
-                         "traffic_GBps": (traffic / ((fwd_ms if dom == "fwd" else bwd_ms) * 1e-3) / 1e9) if traffic else None,
-                         "traffic_frac": (traffic / ((fwd_ms if dom == "fwd" else bwd_ms) * 1e-3) / 1e9 / peak) if traffic else None,
-                         "algorithmic_bytes_per_cell": BYTES_FWD if dom == "fwd" else BYTES_BWD,
-                         "fwd": {"ms": fwd_ms, "GBps": fwd_gbs, "frac": fwd_gbs / peak},
-                         "bwd": {"ms": bwd_ms, "GBps": bwd_gbs, "frac": bwd_gbs / peak},
-                         "step": {"GBps_at_36B_per_cell": step_gbs, "frac": step_gbs / peak}},
-            "gpu_launches": 2 * args.steps,
-            "host_enqueue_ms_per_step": host_ms,
-            "step_ms_median": float(np.median([k[0].elapsed_time(k[2]) for k in kev])),
-            "step_ms_first3": [round(k[0].elapsed_time(k[2]), 4) for k in kev[:3]],
-            "step_ms_max": float(np.max([k[0].elapsed_time(k[2]) for k in kev])),
+                             % (2 * w.theta.numel() * 4 / 1e6, w.cells * 8 / 1e6),
+                       "launch": "forward and backward captured once in two CUDA graphs through the autograd API, "
+                                 "replayed per step" if r["graphed"] else "eager calls",
+                       **({"packing": w.stats} if w.stats else {})},
+            "roofline": rf,
+            "gpu_launches": 2 * steps,
+            "host_enqueue_ms_per_step": r["host_enqueue_ms_per_step"],
+            "step_ms_median": r["step_ms_median"], "step_ms_first3": r["step_ms_first3"],
+            "step_ms_max": r["step_ms_max"], "eager": r["eager"],
             "clocks": clocks,
         }
+        if "graph_error" in r:
+            line["graph_error"] = r["graph_error"]
         if e2e:
             line["e2e"] = e2e
-        if world == 1 and not args.no_cpu_baseline:
+    del r
+
+    # ---- every other BASELINE config under the same clock ---------------------------------------------
+    if not args.no_extras:
+        extras = {}
+        xs = max(3, min(steps, 10))
+        for name in ("c2", "c3", "c4", "c5", "b32"):
+            if name == args.workload:
+                continue
+            try:
+                wk = make_workload(cx, name)
+                rk = time_workload(cx, wk, xs, 3, use_graph=not args.no_graph)
+                ent = {"workload": wk.desc, "pairs_per_gpu": wk.B,
+                       "value": rk["total_cells"] * xs / (rk["ms_total"] * 1e-3), "unit": "cell-updates/s",
+                       "ms_per_step": rk["ms_total"] / xs, "steps": xs, "graphed": rk["graphed"],
+                       "host_enqueue_ms_per_step": rk["host_enqueue_ms_per_step"], "eager": rk["eager"]}
+                if wk.stats:
+                    ent["packing"] = wk.stats
+                if cx.rank == 0:
+                    ent["roofline"] = roofline(cx, wk, rk, traffic_tab)
+                if name == "c5" and not args.no_e2e:
+                    ent["e2e"] = e2e_of(wk, 5)
+                    if cx.world == 1 and not args.no_cpu_baseline:
+                        if _ALL_CPUS:
+                            os.sched_setaffinity(0, _ALL_CPUS)
+                        v, cores, sample, _ = cpu_port_throughput(wk.mode, wk.N, wk.M, wk.xl, wk.yl, target_s=5.0)
+                        ent["cpu_baseline"] = {"value": v, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+                                               "sample": sample}
+                extras[name] = ent
+                del rk, wk
+            except Exception as e:
+                extras[name] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+        if cx.world == 1:
+            for tag, (B, N, M) in (("train_step_c2", (1024, 256, 256)), ("train_step_b32x512", (32, 512, 512))):
+                try:
+                    t = train_step_bench(cx, B, N, M, 10)
+                    t.pop("_keep", None)
+                    extras[tag] = t
+                except Exception as e:
+                    extras[tag] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+                torch.cuda.synchronize()
+                torch.cuda.empty_cache()
+        if cx.rank == 0:
+            line["workloads"] = extras
+
+    if cx.rank == 0:
+        if cx.world == 1 and not args.no_cpu_baseline:
             if _ALL_CPUS:
                 os.sched_setaffinity(0, _ALL_CPUS)        # the CPU baseline gets every host core again
-            xl = None if xlen is None else xlen.cpu().numpy()
-            yl = None if ylen is None else ylen.cpu().numpy()
-            v, cores, sample, _ = cpu_port_throughput(mode, N, M, xl, yl, target_s=args.cpu_seconds)
+            v, cores, sample, _ = cpu_port_throughput(w.mode, w.N, w.M, w.xl, w.yl, target_s=args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "cell-updates/s", "cores": cores, "kind": "port",
                                     "sample": sample}
         print(json.dumps(line))
-    if world > 1:
+    if cx.world > 1:
         dist.destroy_process_group()
     return 0
 

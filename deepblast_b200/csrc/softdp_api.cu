@@ -63,12 +63,7 @@ bool encode_row_map(CUtensorMap* map, const float* ptr, int B, int N, int M, int
     // L2 promotion 256 B: a box row is only 64-128 B, but the neighbouring columns of the row
     // are consumed a few blocks later, and DRAM serves 256-byte pieces far better than 64-byte
     // ones (measured on B200, C2 forward: 0.272 ms with 128 B promotion, 0.246 ms with 256 B)
-    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-    if (const char* e = getenv("B200DP_PROMO")) {
-        const int v = atoi(e);
-        promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-              : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-    }
+    const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -110,8 +105,6 @@ int pick_geometry(const char* fn, int B, int N, int M, int flags, SmemFn smem_of
     const int K = (N + kTile - 1) / kTile;
     int forceW = (flags >> B200DP_WARPS_SHIFT) & 0xF;
     int forceG = (flags >> B200DP_CTAS_SHIFT) & 0xFFFF;
-    if (const char* e = getenv("B200DP_WARPS")) forceW = atoi(e);
-    if (const char* e = getenv("B200DP_CTAS")) forceG = atoi(e);
     double best = 1e300;
     g.W = 0;
     for (int W = 1; W <= 8; W *= 2) {
@@ -162,16 +155,10 @@ int pick_geometry(const char* fn, int B, int N, int M, int flags, SmemFn smem_of
     return 0;
 }
 
-bool env_no_tma() {
-    const char* e = getenv("B200DP_NO_TMA");
-    return e && atoi(e) != 0;
-}
-// B200DP_V1=1 (or flag B200DP_V1_KERNELS) keeps the general kernels on shapes the fast
-// path would take; used by the parity tests to cover both.
-bool env_v1() {
-    const char* e = getenv("B200DP_V1");
-    return e && atoi(e) != 0;
-}
+// Dispatch overrides travel in `flags` (include/b200dp.h); the library reads no environment
+// variables.
+bool no_chained(int flags) { return (flags & B200DP_NO_CHAINED) != 0; }
+int ring_flag(int flags) { return (flags >> B200DP_SQ_RING_SHIFT) & 0xF; }
 
 // Chained backward kernel (softdp_bwd3.cuh).  Same return convention as launch_fwd3.
 template <int RING>
@@ -187,16 +174,13 @@ int launch_bwd3_t(const BwdParams& p, int grid, size_t smem, bool sw, cudaStream
 }
 
 int launch_bwd3(const BwdParams& p, int B, int N, int M, int mode, int flags, cudaStream_t st) {
-    if (const char* e = getenv("B200DP_V3")) if (atoi(e) == 0) return 1;
+    if (no_chained(flags)) return 1;
     DevInfo di;
     if (!dev_info(di)) return 1;
-    int minB = kChainedMinPairsPerSM * di.sms;
-    if (const char* e = getenv("B200DP_V3MIN")) minB = atoi(e);
+    const int minB = (flags & B200DP_FORCE_CHAINED) ? 1 : kChainedMinPairsPerSM * di.sms;
     if (B < minB || N < kTile || M < 64 || M % 32 != 0) return 1;
-    int want_ring = 0;
-    if (const char* e = getenv("B200DP_BRING")) want_ring = atoi(e);
-    int forceG = (flags >> B200DP_CTAS_SHIFT) & 0xFFFF;
-    if (const char* e = getenv("B200DP_CTAS")) forceG = atoi(e);
+    const int want_ring = ring_flag(flags);
+    const int forceG = (flags >> B200DP_CTAS_SHIFT) & 0xFFFF;
     const int rings[4] = {3, 4, 6, 2};     // measured on B200: 3 slots win
     int ring = 0, grid = 0;
     size_t smem = 0;
@@ -237,39 +221,28 @@ int launch_bwd3(const BwdParams& p, int B, int N, int M, int mode, int flags, cu
 // falls through to softdp_fwd2), < 0 (-(1000 + code)) on error.
 template <int NCH, int RING>
 int launch_fwd3_t(const CUtensorMap& tmT, const CUtensorMap& tmA, const CUtensorMap& pfT, const CUtensorMap& pfA,
-                  const FwdParams& p, int grid, size_t smem, bool sw, int dbg, cudaStream_t st) {
+                  const FwdParams& p, int grid, size_t smem, bool sw, cudaStream_t st) {
     int rc = 0;
     auto run = [&](auto kern) {
         rc = set_smem(kern, smem, "b200dp_fwd");
         if (!rc) kern<<<grid, 32, smem, st>>>(tmT, tmA, pfT, pfA, p);
     };
-    if (dbg == 1) run(softdp_fwd3_kernel<false, NCH, RING, 1>);
-    else if (dbg == 2) run(softdp_fwd3_kernel<false, NCH, RING, 2>);
-    else if (dbg == 3) run(softdp_fwd3_kernel<false, NCH, RING, 3>);
-    else if (sw) run(softdp_fwd3_kernel<true, NCH, RING>);
+    if (sw) run(softdp_fwd3_kernel<true, NCH, RING>);
     else run(softdp_fwd3_kernel<false, NCH, RING>);
     return rc;
 }
 
 int launch_fwd3(const CUtensorMap& tmT, const CUtensorMap& tmA, FwdParams p, int B, int N, int M, int mode,
                 int flags, cudaStream_t st) {
-    if (const char* e = getenv("B200DP_V3")) if (atoi(e) == 0) return 1;
+    if (no_chained(flags)) return 1;
     DevInfo di;
     if (!dev_info(di)) return 1;
-    int minB = kChainedMinPairsPerSM * di.sms;
-    if (const char* e = getenv("B200DP_V3MIN")) minB = atoi(e);
-    if (B < minB || N < kTile) return 1;
-    const int K = (N + kTile - 1) / kTile;
-    int nch = 1;     // measured on B200: two chains per warp lose to one (the kernel is bound by the memory system, not by issue latency)
-    if (const char* e = getenv("B200DP_NCH")) nch = atoi(e) == 2 ? 2 : 1;
-    if (M < 32 * nch + 32) nch = 1;
-    if (M < 64) return 1;
-    int want_ring = 0;
-    if (const char* e = getenv("B200DP_RING")) want_ring = atoi(e);
-    int forceG = (flags >> B200DP_CTAS_SHIFT) & 0xFFFF;
-    if (const char* e = getenv("B200DP_CTAS")) forceG = atoi(e);
-    int dbg = 0;
-    if (const char* e = getenv("B200DP_DBG")) dbg = atoi(e);
+    const int minB = (flags & B200DP_FORCE_CHAINED) ? 1 : kChainedMinPairsPerSM * di.sms;
+    if (B < minB || N < kTile || M < 64) return 1;
+    // (two chains per warp, NCH = 2, lose to one: the kernel is bound by the memory system, not by
+    // issue latency; only NCH = 1 is instantiated)
+    const int want_ring = ring_flag(flags);
+    const int forceG = (flags >> B200DP_CTAS_SHIFT) & 0xFFFF;
     // measured on B200 with the two-state Q: 4 slots (two events of lead) beat 3 by 2-4 %
     const int rings[4] = {4, 3, 6, 8};
     int ring = 0, grid = 0;
@@ -278,7 +251,7 @@ int launch_fwd3(const CUtensorMap& tmT, const CUtensorMap& tmA, FwdParams p, int
     for (int ri = 0; ri < 4; ++ri) {
         const int r = rings[ri];
         if (want_ring && r != want_ring) continue;
-        const size_t sm = (size_t)r * nch * 4096 + (size_t)r * 8 + 16 + (size_t)M * 4 + 128;
+        const size_t sm = (size_t)r * 4096 + (size_t)r * 8 + 16 + (size_t)M * 4 + 128;
         if (sm > (size_t)di.smem_optin) continue;
         int per_sm = (int)((size_t)di.smem_per_sm / (sm + 1024));
         if (per_sm > 32) per_sm = 32;
@@ -296,31 +269,12 @@ int launch_fwd3(const CUtensorMap& tmT, const CUtensorMap& tmA, FwdParams p, int
     }
     if (!ring) return 1;
     if (forceG > 0) grid = forceG;
-    // optional wide L2 prefetch boxes (B200DP_PFW columns x 32 nch rows, B200DP_PFD tiles ahead)
-    int pfw = 0, pfd = 8;
-    if (const char* e = getenv("B200DP_PFW")) pfw = atoi(e);
-    if (const char* e = getenv("B200DP_PFD")) pfd = atoi(e);
-    CUtensorMap pfT, pfA;
-    memset(&pfT, 0, sizeof(pfT));
-    memset(&pfA, 0, sizeof(pfA));
     p.pf_tiles = 0;
     p.pf_dist = 0;
-    if (pfw >= 16 && pfw <= 256 && pfw % 16 == 0 && M % pfw == 0 && pfd >= 0 &&
-        encode_row_map(&pfT, p.theta, B, N, M, pfw, 32 * nch) && encode_row_map(&pfA, p.A, B, N, M, pfw, 32 * nch)) {
-        p.pf_tiles = pfw / 16;
-        p.pf_dist = pfd;
-    } else {
-        pfT = tmT;
-        pfA = tmA;
-    }
     const bool sw = mode == B200DP_MODE_SW;
     int rc = 0;
-#define B200DP_F3(NCH_, RING_) rc = launch_fwd3_t<NCH_, RING_>(tmT, tmA, pfT, pfA, p, grid, smem, sw, dbg, st)
-    if (nch == 2) {
-        if (ring == 8) B200DP_F3(2, 8); else if (ring == 6) B200DP_F3(2, 6); else if (ring == 4) B200DP_F3(2, 4); else B200DP_F3(2, 3);
-    } else {
-        if (ring == 8) B200DP_F3(1, 8); else if (ring == 6) B200DP_F3(1, 6); else if (ring == 4) B200DP_F3(1, 4); else B200DP_F3(1, 3);
-    }
+#define B200DP_F3(RING_) rc = launch_fwd3_t<1, RING_>(tmT, tmA, tmT, tmA, p, grid, smem, sw, st)
+    if (ring == 8) B200DP_F3(8); else if (ring == 6) B200DP_F3(6); else if (ring == 4) B200DP_F3(4); else B200DP_F3(3);
 #undef B200DP_F3
     if (rc) return -(1000 + rc);
     cudaError_t e = cudaGetLastError();
@@ -373,12 +327,12 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
     CUtensorMap tmT, tmA;
     memset(&tmT, 0, sizeof(tmT));
     memset(&tmA, 0, sizeof(tmA));
-    bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma() && (M % 4 == 0) && M >= kTile && N >= kTile &&
+    bool tma = !(flags & B200DP_NO_TMA) && (M % 4 == 0) && M >= kTile && N >= kTile &&
                aligned(theta, 16) && aligned(A, 16);
-    const bool fast = tma && !(flags & B200DP_V1_KERNELS) && !env_v1() && N >= kG && M >= 2 * kG;
+    const bool fast = tma && !(flags & B200DP_V1_KERNELS) && N >= kG && M >= 2 * kG;
     if (fast && encode_row_map(&tmT, theta, B, N, M, kG) && encode_row_map(&tmA, A, B, N, M, kG)) {
         // large batches of equal-size lattices: chained single-warp kernel (softdp_fwd3.cuh)
-        if (!xlen && !ylen && M % 16 == 0 && !((flags >> B200DP_WARPS_SHIFT) & 0xF) && !getenv("B200DP_WARPS")) {
+        if (!xlen && !ylen && M % 16 == 0 && !((flags >> B200DP_WARPS_SHIFT) & 0xF)) {
             int rc3 = launch_fwd3(tmT, tmA, p, B, N, M, mode, flags, st);
             if (rc3 <= 0) return rc3 < 0 ? -rc3 - 1000 : 0;    // 0 = launched, < 0 = error, > 0 = not applicable
         }
@@ -389,8 +343,7 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
         if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<3>, g2, xlen || ylen)) return rc;
         int ring = 3;
         {
-            int want = 8;
-            if (const char* e = getenv("B200DP_RING")) want = atoi(e);
+            const int want = ring_flag(flags) ? ring_flag(flags) : 8;
             Geometry gt;
             if (want >= 4 && pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<4>, gt, xlen || ylen) == 0 &&
                 gt.W == g2.W && gt.grid >= g2.grid) {
@@ -409,22 +362,13 @@ int b200dp_fwd(const float* theta, const float* A, float* Q, float* Vt, const in
                 }
             }
         }
-        int dbg = 0;
-        if (const char* e = getenv("B200DP_DBG")) dbg = atoi(e);     // diagnostics: see softdp_fwd2.cuh
         int rc2 = 0;
         auto run = [&](auto kern) {
             rc2 = set_smem(kern, g2.smem, "b200dp_fwd");
             if (!rc2) kern<<<g2.grid, 32 * g2.W, g2.smem, st>>>(tmT, tmA, p);
         };
         const bool sw = mode == B200DP_MODE_SW;
-        if (dbg >= 1 && dbg <= 3) {
-            Geometry g3;
-            if (int rc = pick_geometry("b200dp_fwd", B, N, M, flags, fwd2_smem_bytes<3>, g3, xlen || ylen)) return rc;
-            g2 = g3;
-            if (dbg == 1) run(softdp_fwd2_kernel<false, 3, 1>);
-            else if (dbg == 2) run(softdp_fwd2_kernel<false, 3, 2>);
-            else run(softdp_fwd2_kernel<false, 3, 3>);
-        } else if (ring == 8) {
+        if (ring == 8) {
             sw ? run(softdp_fwd2_kernel<true, 8>) : run(softdp_fwd2_kernel<false, 8>);
         } else if (ring == 6) {
             sw ? run(softdp_fwd2_kernel<true, 6>) : run(softdp_fwd2_kernel<false, 6>);
@@ -484,16 +428,15 @@ static int bwd_impl(const float* Et, long long et_stride, const float* Q, float*
     p.i0 = mode == B200DP_MODE_SW ? 2 : 1;
     p.flags = flags;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const bool tma = !(flags & B200DP_NO_TMA) && !env_no_tma();
+    const bool tma = !(flags & B200DP_NO_TMA);
     Geometry g;
-    if (tma && !(flags & B200DP_V1_KERNELS) && !env_v1() && !xlen && !ylen && !((flags >> B200DP_WARPS_SHIFT) & 0xF) &&
-        !getenv("B200DP_WARPS")) {
+    if (tma && !(flags & B200DP_V1_KERNELS) && !xlen && !ylen && !((flags >> B200DP_WARPS_SHIFT) & 0xF)) {
         // large batches of equal-size lattices: chained single-warp kernel (softdp_bwd3.cuh)
         int rc3 = launch_bwd3(p, B, N, M, mode, flags, st);
         if (rc3 == 0 && wrote_ei && Ei) *wrote_ei = 1;      // only the chained kernel writes the second copy
         if (rc3 <= 0) return rc3 < 0 ? -rc3 - 1000 : 0;
     }
-    if (tma && !(flags & B200DP_V1_KERNELS) && !env_v1() && M >= 2 * kG) {
+    if (tma && !(flags & B200DP_V1_KERNELS) && M >= 2 * kG) {
         if (int rc = pick_geometry("b200dp_bwd", B, N, M, flags, bwd2_smem_bytes, g, xlen || ylen)) return rc;
         if (mode == B200DP_MODE_SW) {
             if (int rc = set_smem(softdp_bwd2_kernel<true>, g.smem, "b200dp_bwd")) return rc;
@@ -535,7 +478,7 @@ int b200dp_adj_fwd(const float* Q, const float* Ztheta, const float* ZA, float* 
     p.d = PairDims{xlen, ylen, B, N, M};
     p.ql = q_layout(N, M);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (!(flags & B200DP_NO_TMA) && !env_no_tma()) {
+    if (!(flags & B200DP_NO_TMA)) {
         if (int rc = set_smem(softdp_adj_fwd_kernel<true>, g.smem, "b200dp_adj_fwd")) return rc;
         softdp_adj_fwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(p);
     } else {
@@ -564,7 +507,7 @@ int b200dp_adj_bwd(const float* E, const float* Q, const float* Qd, float* Ed, c
     p.d = PairDims{xlen, ylen, B, N, M};
     p.ql = q_layout(N, M);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (!(flags & B200DP_NO_TMA) && !env_no_tma()) {
+    if (!(flags & B200DP_NO_TMA)) {
         if (int rc = set_smem(softdp_adj_bwd_kernel<true>, g.smem, "b200dp_adj_bwd")) return rc;
         softdp_adj_bwd_kernel<true><<<g.grid, 32 * g.W, g.smem, st>>>(p);
     } else {
@@ -606,15 +549,13 @@ int b200dp_traceback(const float* grad, long long sb, long long si, long long sj
 
 // ---- chained adjoint pair (double backward on large batches of equal-size lattices) ----------
 static bool adj3_shape_ok(int B, int N, int M) {
-    if (const char* e = getenv("B200DP_V3")) if (atoi(e) == 0) return false;
     DevInfo di;
     if (!dev_info(di)) return false;
-    int minB = 1;      // measured on B200: the chained adjoint pair beats the general kernels at every batch size
-    if (const char* e = getenv("B200DP_V3MIN")) minB = atoi(e);
-    return B >= minB && N >= kTile && M >= 64 && M % 32 == 0 && get_encode() != nullptr;
+    // (measured on B200: the chained adjoint pair beats the general kernels at every batch size)
+    return B >= 1 && N >= kTile && M >= 64 && M % 32 == 0 && get_encode() != nullptr;
 }
 
-static int chained_grid(int B, size_t smem, int& grid) {
+static int chained_grid(int B, size_t smem, int& grid, int flags) {
     DevInfo di;
     if (!dev_info(di)) return -1;
     if (smem > (size_t)di.smem_optin) return -1;
@@ -624,7 +565,7 @@ static int chained_grid(int B, size_t smem, int& grid) {
     const long long resident = (long long)di.sms * per_sm;
     const long long rounds = (B + resident - 1) / resident;
     grid = (int)((B + rounds - 1) / rounds);
-    if (const char* e = getenv("B200DP_CTAS")) if (atoi(e) > 0) grid = atoi(e);
+    if ((flags >> B200DP_CTAS_SHIFT) & 0xFFFF) grid = (flags >> B200DP_CTAS_SHIFT) & 0xFFFF;
     return (int)rounds;
 }
 
@@ -659,7 +600,7 @@ int b200dp_adj_fwd3(const float* Q, const float* Zt, const float* ZA, const floa
     // three Q tile slots unless two save a whole round of CTAs (M >= 512 at 1024 pairs)
     int g3 = 0, g2 = 0;
     const size_t s3 = fwd3_smem_bytes<1, 3, true, 3>(M), s2 = fwd3_smem_bytes<1, 3, true, 2>(M);
-    const int r3 = chained_grid(B, s3, g3), r2 = chained_grid(B, s2, g2);
+    const int r3 = chained_grid(B, s3, g3, flags), r2 = chained_grid(B, s2, g2, flags);
     if (r2 < 0) return fail(-3, "b200dp_adj_fwd3: M too large for shared memory");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (r3 > 0 && r3 <= r2) {
@@ -697,7 +638,7 @@ int b200dp_adj_bwd3(const float* Q, const float* QdE, float* Ed, float* Ed_inter
     // three Q + QdE slots unless the smaller ring saves a whole round of CTAs
     int g3 = 0, g2 = 0;
     const size_t s3 = bwd3_smem_bytes<3, true>(M), s2 = bwd3_smem_bytes<2, true>(M);
-    const int r3 = chained_grid(B, s3, g3), r2 = chained_grid(B, s2, g2);
+    const int r3 = chained_grid(B, s3, g3, flags), r2 = chained_grid(B, s2, g2, flags);
     if (r2 < 0) return fail(-3, "b200dp_adj_bwd3: M too large for shared memory");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (r3 > 0 && r3 <= r2) {
@@ -724,7 +665,13 @@ int b200dp_mxent_fwd(const float* Ytrue, const float* Ypred, long long pb, long 
     p.Ytrue = Ytrue; p.Ypred = Ypred; p.G = G; p.xlen = xlen; p.ylen = ylen;
     p.pb = pb; p.pi = pi; p.B = B; p.N = N; p.M = M;
     p.pair_loss = pair_loss; p.pair_count = pair_count;
-    softdp_mxent_fwd_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // the slabs accumulate into pair_loss / pair_count: start from zero
+    cudaError_t e0 = cudaMemsetAsync(pair_loss, 0, (size_t)B * 4, st);
+    if (e0 == cudaSuccess) e0 = cudaMemsetAsync(pair_count, 0, (size_t)B * 4, st);
+    if (e0 != cudaSuccess) return cuda_fail(e0, "b200dp_mxent_fwd memset");
+    softdp_mxent_fwd_kernel<<<dim3((N + kLossRows - 1) / kLossRows, B), 256, 0, st>>>(p);
+    softdp_mxent_fin_kernel<<<(B + 255) / 256 < 64 ? (B + 255) / 256 : 64, 256, 0, st>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "b200dp_mxent_fwd launch");
     return 0;
@@ -740,7 +687,7 @@ int b200dp_mxent_bwd(const float* Ytrue, const float* Ypred, long long pb, long 
     p.Ytrue = Ytrue; p.Ypred = Ypred; p.G = G; p.xlen = xlen; p.ylen = ylen;
     p.pb = pb; p.pi = pi; p.B = B; p.N = N; p.M = M;
     p.pair_count = const_cast<float*>(pair_count); p.gout = gout; p.grad = grad;
-    softdp_mxent_bwd_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    softdp_mxent_bwd_kernel<<<dim3((N + kLossRows - 1) / kLossRows, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "b200dp_mxent_bwd launch");
     return 0;

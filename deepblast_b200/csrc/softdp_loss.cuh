@@ -6,9 +6,9 @@
 //   l_b   = -mean over {(i,j) : i < xlen_b, j < ylen_b, G[b,i,j] != 0} of
 //            Ytrue log Yp + (1 - Ytrue) log(1 - Yp)
 //   loss  = mean_b l_b
-// Here one CTA per pair reduces sum and count in one pass over the three tensors (the step
-// right after the DP backward: Ypred is read in place from the padded E, any row stride),
-// and the backward writes dloss/dYpred densely (zeros outside the mask) in one more pass.
+// Here one launch reduces every pair's sum and count in one pass over the three tensors (the
+// step right after the DP backward: Ypred is read in place, any row stride), and the backward
+// writes dloss/dYpred densely (zeros outside the mask) in one more pass.
 #pragma once
 #include "softdp_common.cuh"
 
@@ -44,22 +44,30 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return s;
 }
 
-// One CTA per pair; warp w takes rows w, w + 8, ...; lanes stride the columns, so every
-// access is a coalesced 128-byte piece and no index needs a division.
+// Grid (row slabs, pairs): a CTA takes kLossRows rows of one pair, warp w rows w, w + 8, ... of
+// the slab; lanes stride the columns, so every access is a coalesced 128-byte piece and no
+// index needs a division.  Slabs add their partial (sum, count) to the pair's totals with
+// atomics (pair_sum / pair_count zero-filled by the caller), a one-CTA kernel then forms
+// l_b / B.  (One CTA per pair, as in round 1, left a B = 32 batch on 32 of 148 SMs.)
+constexpr int kLossRows = 32;
+
 __global__ void __launch_bounds__(256) softdp_mxent_fwd_kernel(LossParams p) {
     __shared__ float red[8];
-    const int b = blockIdx.x;
-    const int n = p.xlen ? min(p.xlen[b], p.N) : p.N;
-    const int m = p.ylen ? min(p.ylen[b], p.M) : p.M;
+    const int b = blockIdx.y;
+    const int n = p.xlen ? min(max(p.xlen[b], 0), p.N) : p.N;
+    const int m = p.ylen ? min(max(p.ylen[b], 0), p.M) : p.M;
+    const int i0 = blockIdx.x * kLossRows, i1 = min(i0 + kLossRows, n);
+    if (i0 >= n) return;
     const float* yt = p.Ytrue + (long long)b * p.N * p.M;
     const float* gm = p.G ? p.G + (long long)b * p.N * p.M : nullptr;
     const float* yp = p.Ypred + (long long)b * p.pb;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     float s = 0.f, c = 0.f;
-    for (int i = w; i < n; i += nw) {
+    for (int i = i0 + w; i < i1; i += nw) {
         const float* ytr = yt + (long long)i * p.M;
         const float* gmr = gm ? gm + (long long)i * p.M : nullptr;
         const float* ypr = yp + (long long)i * p.pi;
+#pragma unroll 4
         for (int j = lane; j < m; j += 32) {
             if (!gmr || gmr[j] != 0.f) {
                 const float y = ytr[j];
@@ -72,26 +80,33 @@ __global__ void __launch_bounds__(256) softdp_mxent_fwd_kernel(LossParams p) {
     s = block_sum(s, red);
     c = block_sum(c, red);
     if (threadIdx.x == 0) {
-        p.pair_loss[b] = -(s / c) / (float)p.B;      // mean of an empty selection is NaN, as in torch
-        p.pair_count[b] = c;
+        atomicAdd(p.pair_loss + b, s);               // raw sum here; softdp_mxent_fin_kernel turns it into l_b / B
+        atomicAdd(p.pair_count + b, c);
     }
 }
 
+__global__ void softdp_mxent_fin_kernel(LossParams p) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < p.B; b += gridDim.x * blockDim.x)
+        p.pair_loss[b] = -(p.pair_loss[b] / p.pair_count[b]) / (float)p.B;   // mean of an empty selection is NaN, as in torch
+}
+
 __global__ void __launch_bounds__(256) softdp_mxent_bwd_kernel(LossParams p) {
-    const int b = blockIdx.x;
-    const int n = p.xlen ? min(p.xlen[b], p.N) : p.N;
-    const int m = p.ylen ? min(p.ylen[b], p.M) : p.M;
+    const int b = blockIdx.y;
+    const int n = p.xlen ? min(max(p.xlen[b], 0), p.N) : p.N;
+    const int m = p.ylen ? min(max(p.ylen[b], 0), p.M) : p.M;
     const float* yt = p.Ytrue + (long long)b * p.N * p.M;
     const float* gm = p.G ? p.G + (long long)b * p.N * p.M : nullptr;
     const float* yp = p.Ypred + (long long)b * p.pb;
     float* gr = p.grad + (long long)b * p.N * p.M;
     const float scale = -p.gout[0] / (p.pair_count[b] * (float)p.B);
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int i = w; i < p.N; i += nw) {
+    const int i0 = blockIdx.x * kLossRows, i1 = min(i0 + kLossRows, p.N);
+    for (int i = i0 + w; i < i1; i += nw) {
         const float* ytr = yt + (long long)i * p.M;
         const float* gmr = gm ? gm + (long long)i * p.M : nullptr;
         const float* ypr = yp + (long long)i * p.pi;
         float* grr = gr + (long long)i * p.M;
+#pragma unroll 4
         for (int j = lane; j < p.M; j += 32) {
             float g = 0.f;
             if (i < n && j < m && (!gmr || gmr[j] != 0.f)) {

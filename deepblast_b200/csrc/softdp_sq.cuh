@@ -62,8 +62,11 @@ static_assert(sizeof(StripRec) == 64, "StripRec is 64 bytes");
 struct SqParams {
     const StripRec* tab;
     int nstrips;
-    unsigned epoch;              // tag of this launch's boundary words (never 0)
-    unsigned long long* ctl;     // ticket counter (low 32 bits) | exited warps (high 32 bits); self-resetting
+    unsigned long long* ctl;     // ctl[0]: ticket counter (low 32 bits) | exited warps (high 32 bits), self-resetting;
+                                 // ctl[1]: launches done on this workspace -- the tag of a launch's boundary words
+                                 // is ctl[1] + 1 (never 0, so a zero-filled workspace holds no valid word); the last
+                                 // warp to leave bumps it, so the tag lives on the DEVICE and a launch captured in a
+                                 // CUDA graph gets a fresh tag at every replay
     unsigned long long* bnd;     // boundary scratch
     // forward:          theta, A -> Q, Vt
     // adjoint forward:  theta = Ztheta (interior layout), A = ZA or null, E or null, Qin -> Q = Qd * E, Vt = Vtd
@@ -116,11 +119,17 @@ __device__ __forceinline__ StripRec sq_load_rec(const StripRec* tab, int tk, int
 
 // A warp leaves: count it, and the last one to leave resets the control word for the next launch
 // (every pull of every warp precedes its own exit on the same address, so nothing is pending).
-__device__ __forceinline__ void sq_exit(unsigned long long* ctl) {
+__device__ __forceinline__ void sq_exit(unsigned long long* ctl, unsigned epoch) {
     if ((threadIdx.x & 31) == 0) {
         const unsigned long long old = atomicAdd(ctl, 1ull << 32);
-        if ((unsigned)(old >> 32) == gridDim.x - 1) atomicExch(ctl, 0ull);
+        if ((unsigned)(old >> 32) == gridDim.x - 1) {
+            ctl[1] = epoch;                      // every warp of this launch has read it (they all started)
+            atomicExch(ctl, 0ull);
+        }
     }
+}
+__device__ __forceinline__ unsigned sq_epoch(const unsigned long long* ctl) {
+    return (unsigned)ld_relaxed_gpu_u64(ctl + 1) + 1u;
 }
 
 // Boundary entries of one block (16 columns): `pfv` was loaded one block ahead by lanes 0..15;
@@ -166,7 +175,7 @@ __global__ void __launch_bounds__(32) softdp_sq_fwd_kernel(const SqParams p) {
     constexpr int FDBG = STOREQ ? 0 : 4;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int t = threadIdx.x, g = t >> 4, tp = t & 15, r8 = t >> 2, ch = t & 3;
-    const unsigned epoch = p.epoch;
+    const unsigned epoch = sq_epoch(p.ctl);
 
     unsigned char* ring = smem_raw;
     float* qring = reinterpret_cast<float*>(smem_raw + (size_t)RING * kSlot);
@@ -411,7 +420,7 @@ __global__ void __launch_bounds__(32) softdp_sq_fwd_kernel(const SqParams p) {
         nxt_ready = false;
         nxt.rows = 0;
     }
-    sq_exit(p.ctl);
+    sq_exit(p.ctl, epoch);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -460,7 +469,7 @@ __global__ void __launch_bounds__(32) softdp_sq_bwd_kernel(const SqParams p) {
     constexpr int kSlotElems = kDiagElems * (ADJ ? 2 : 1);      // [Q tile | QdE tile]
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int t = threadIdx.x, u = 31 - t;
-    const unsigned epoch = p.epoch;
+    const unsigned epoch = sq_epoch(p.ctl);
 
     float* qring = reinterpret_cast<float*>(smem_raw);
     float* stage = qring + RING * kSlotElems;
@@ -668,7 +677,7 @@ __global__ void __launch_bounds__(32) softdp_sq_bwd_kernel(const SqParams p) {
         nxt_ready = false;
         nxt.rows = 0;
     }
-    sq_exit(p.ctl);
+    sq_exit(p.ctl, epoch);
 }
 
 }  // namespace b200dp

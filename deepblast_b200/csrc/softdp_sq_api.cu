@@ -61,21 +61,19 @@ int sq_launch(Kern k, size_t smem, const SqParams& p, int flags, cudaStream_t st
     return 0;
 }
 
-int sq_check(const char* fn, const void* tab, int nstrips, const void* ws, unsigned epoch) {
+int sq_check(const char* fn, const void* tab, int nstrips, const void* ws) {
     if (nstrips < 0) return fail(-1, std::string(fn) + ": nstrips < 0");
     if (nstrips == 0) return 0;
     if (!tab || !ws) return fail(-1, std::string(fn) + ": null plan table / workspace");
     if (!aligned(tab, 16) || !aligned(ws, 256)) return fail(-1, std::string(fn) + ": table must be 16-byte, workspace 256-byte aligned");
-    if (epoch == 0) return fail(-1, std::string(fn) + ": epoch must not be 0 (a zeroed workspace would read as valid)");
     return 0;
 }
 
-SqParams sq_params(const void* tab, int nstrips, void* ws, unsigned epoch) {
+SqParams sq_params(const void* tab, int nstrips, void* ws) {
     SqParams p;
     memset(&p, 0, sizeof(p));
     p.tab = static_cast<const StripRec*>(tab);
     p.nstrips = nstrips;
-    p.epoch = epoch;
     p.ctl = static_cast<unsigned long long*>(ws);
     p.bnd = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(ws) + kSqCtlBytes);
     return p;
@@ -253,15 +251,15 @@ int b200dp_sq_resident_warps(int kind) {
     return di.sms * occ;
 }
 
-int b200dp_sq_fwd(const void* tab, int nstrips, void* workspace, unsigned epoch, const float* theta, const float* A,
+int b200dp_sq_fwd(const void* tab, int nstrips, void* workspace, const float* theta, const float* A,
                   float* Q, float* Vt, int mode, int flags, void* stream) {
-    if (int rc = sq_check("b200dp_sq_fwd", tab, nstrips, workspace, epoch)) return rc;
+    if (int rc = sq_check("b200dp_sq_fwd", tab, nstrips, workspace)) return rc;
     if (mode != B200DP_MODE_NW && mode != B200DP_MODE_SW) return fail(-1, "b200dp_sq_fwd: bad mode");
     if (nstrips == 0) return 0;
     if (!theta || !A || !Vt) return fail(-1, "b200dp_sq_fwd: null pointer");
     if (!aligned(theta, 16) || !aligned(A, 16) || (Q && !aligned(Q, 16)))
         return fail(-1, "b200dp_sq_fwd: theta, A and Q must be 16-byte aligned");
-    SqParams p = sq_params(tab, nstrips, workspace, epoch);
+    SqParams p = sq_params(tab, nstrips, workspace);
     p.dbg = (flags >> B200DP_SQ_DBG_SHIFT) & 0xF;
     p.trace = static_cast<unsigned long long*>(g_trace);
     p.theta = theta;
@@ -295,14 +293,14 @@ int b200dp_sq_fwd(const void* tab, int nstrips, void* workspace, unsigned epoch,
 #undef B200DP_SQF
 }
 
-int b200dp_sq_bwd(const void* tab, int nstrips, void* workspace, unsigned epoch, const float* Et, long long et_stride,
+int b200dp_sq_bwd(const void* tab, int nstrips, void* workspace, const float* Et, long long et_stride,
                   const float* Q, float* E, int mode, int flags, void* stream) {
-    if (int rc = sq_check("b200dp_sq_bwd", tab, nstrips, workspace, epoch)) return rc;
+    if (int rc = sq_check("b200dp_sq_bwd", tab, nstrips, workspace)) return rc;
     if (mode != B200DP_MODE_NW && mode != B200DP_MODE_SW) return fail(-1, "b200dp_sq_bwd: bad mode");
     if (nstrips == 0) return 0;
     if (!Et || !Q || !E) return fail(-1, "b200dp_sq_bwd: null pointer");
     if (!aligned(Q, 16)) return fail(-1, "b200dp_sq_bwd: Q storage must be 16-byte aligned");
-    SqParams p = sq_params(tab, nstrips, workspace, epoch);
+    SqParams p = sq_params(tab, nstrips, workspace);
     p.dbg = (flags >> B200DP_SQ_DBG_SHIFT) & 0xF;
     p.trace = static_cast<unsigned long long*>(g_trace);
     p.Et = Et;
@@ -331,14 +329,14 @@ int b200dp_sq_bwd(const void* tab, int nstrips, void* workspace, unsigned epoch,
 #undef B200DP_SQB
 }
 
-int b200dp_sq_adj_fwd(const void* tab, int nstrips, void* workspace, unsigned epoch, const float* Q, const float* Zt,
+int b200dp_sq_adj_fwd(const void* tab, int nstrips, void* workspace, const float* Q, const float* Zt,
                       const float* ZA, const float* E, float* Vtd, float* QdE, int flags, void* stream) {
-    if (int rc = sq_check("b200dp_sq_adj_fwd", tab, nstrips, workspace, epoch)) return rc;
+    if (int rc = sq_check("b200dp_sq_adj_fwd", tab, nstrips, workspace)) return rc;
     if (nstrips == 0) return 0;
     if (!Q || !Zt || !Vtd || !QdE) return fail(-1, "b200dp_sq_adj_fwd: null pointer");
     if (!aligned(Q, 16) || !aligned(QdE, 16) || !aligned(Zt, 16) || (ZA && !aligned(ZA, 16)) || (E && !aligned(E, 16)))
         return fail(-1, "b200dp_sq_adj_fwd: pointers must be 16-byte aligned");
-    SqParams p = sq_params(tab, nstrips, workspace, epoch);
+    SqParams p = sq_params(tab, nstrips, workspace);
     p.dbg = (flags >> B200DP_SQ_DBG_SHIFT) & 0xF;
     p.trace = static_cast<unsigned long long*>(g_trace);
     p.theta = Zt;
@@ -352,13 +350,13 @@ int b200dp_sq_adj_fwd(const void* tab, int nstrips, void* workspace, unsigned ep
                      "b200dp_sq_adj_fwd");
 }
 
-int b200dp_sq_adj_bwd(const void* tab, int nstrips, void* workspace, unsigned epoch, const float* Q, const float* QdE,
+int b200dp_sq_adj_bwd(const void* tab, int nstrips, void* workspace, const float* Q, const float* QdE,
                       float* Ed, int flags, void* stream) {
-    if (int rc = sq_check("b200dp_sq_adj_bwd", tab, nstrips, workspace, epoch)) return rc;
+    if (int rc = sq_check("b200dp_sq_adj_bwd", tab, nstrips, workspace)) return rc;
     if (nstrips == 0) return 0;
     if (!Q || !QdE || !Ed) return fail(-1, "b200dp_sq_adj_bwd: null pointer");
     if (!aligned(Q, 16) || !aligned(QdE, 16)) return fail(-1, "b200dp_sq_adj_bwd: Q / QdE storage must be 16-byte aligned");
-    SqParams p = sq_params(tab, nstrips, workspace, epoch);
+    SqParams p = sq_params(tab, nstrips, workspace);
     p.dbg = (flags >> B200DP_SQ_DBG_SHIFT) & 0xF;
     p.trace = static_cast<unsigned long long*>(g_trace);
     p.Qin = Q;

@@ -9,6 +9,17 @@ from . import _lib
 from .ops import _ptr
 
 
+def _fit(t, shape, name):
+    if t.dim() != 3 or t.shape[0] != shape[0]:
+        raise RuntimeError(f"{name} must be [B, n, m] with B = {shape[0]}, got {tuple(t.shape)}")
+    if tuple(t.shape) == tuple(shape):
+        return t.contiguous()
+    out = torch.zeros(tuple(shape), dtype=t.dtype, device=t.device)
+    n, m = min(shape[1], t.shape[1]), min(shape[2], t.shape[2])
+    out[:, :n, :m] = t[:, :n, :m]
+    return out
+
+
 class _MatrixCrossEntropyFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Ypred, Ytrue, G, xlen, ylen):
@@ -52,9 +63,16 @@ class MatrixCrossEntropy:
         if Ypred.dtype != torch.float32:
             raise TypeError("CUDA variant only supports torch.float32 type")
         dev = Ypred.device
+        if Ypred.dim() != 3:
+            raise RuntimeError("Ypred must be [B, N, M]")
         B = Ypred.shape[0]
-        Ytrue = Ytrue.to(device=dev, dtype=torch.float32).contiguous()
-        G = None if G is None else G.to(device=dev, dtype=torch.float32).contiguous()
+        # the kernels index all three tensors with Ypred's N and M: a differently padded Ytrue / G
+        # (fine for the reference, which slices each tensor on its own, losses.py:28-40) is cut or
+        # zero-padded to Ypred's shape first; cells beyond x_len / y_len are never read
+        Ytrue = _fit(Ytrue.to(device=dev, dtype=torch.float32), Ypred.shape, "Ytrue")
+        G = None if G is None else _fit(G.to(device=dev, dtype=torch.float32), Ypred.shape, "G")
+        if len(x_len) != B or len(y_len) != B:
+            raise RuntimeError(f"x_len / y_len must hold one length per pair ({B})")
         xlen = torch.as_tensor(x_len, dtype=torch.int32).reshape(B).to(dev)
         ylen = torch.as_tensor(y_len, dtype=torch.int32).reshape(B).to(dev)
         return _MatrixCrossEntropyFn.apply(Ypred, Ytrue, G, xlen, ylen)

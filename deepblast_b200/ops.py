@@ -17,8 +17,10 @@ import torch
 from . import _lib
 
 MODES = {"nw": 0, "sw": 1, 0: 0, 1: 1}
+NO_CHAINED = 0x1
 NO_TMA = 0x2
 V1_KERNELS = 0x4
+FORCE_CHAINED = 0x8
 
 
 def _ptr(t):
@@ -209,7 +211,7 @@ def adjoint_backward_pass(E, Q, Qd, xlen=None, ylen=None, flags=0):
     return Ed
 
 
-def adjoint_pair_fast(Q, E, Ztheta, ZA=None, N=None, flags=0, interior=False, Ei=None, interior_out=False):
+def adjoint_pair_fast(Q, E, Ztheta, ZA=None, N=None, flags=0, interior=False, Ei=None, interior_out=False, dims=None):
     """Both adjoint sweeps on the chained kernels (large batches of equal-size lattices):
     Q (strip-major), E [B,N+2,M+2], Ztheta [B,N+2,M+2] (or, with interior=True, its interior
     [B,N,M]; None = zeros), ZA [B,N,M] or None (= zeros) -> (Vtd [B], Ed [B,N+2,M+2]), or
@@ -217,14 +219,20 @@ def adjoint_pair_fast(Q, E, Ztheta, ZA=None, N=None, flags=0, interior=False, Ei
     The forward sweep multiplies Qd by E on the fly (it reads the interiors of Ztheta and E
     as contiguous [B,N,M] tensors through TMA), so the backward sweep needs Q and that
     product only."""
-    B, N2, M2 = E.shape
-    N, M = N2 - 2, M2 - 2
-    if Q.dim() != 5 or not _is_engine_q(Q, N, M) or not Q.is_cuda:
+    # (dims = (B, N, M) with E = None: the caller holds the interior Ei only, no padded E exists)
+    if dims is not None:
+        B, N, M = dims
+        N2, M2 = N + 2, M + 2
+    else:
+        B, N2, M2 = E.shape
+        N, M = N2 - 2, M2 - 2
+    if Q.dim() != 5 or not _is_engine_q(Q, N, M) or not Q.is_cuda or (flags & NO_CHAINED):
         return None
     with torch.cuda.device(Q.device):
         if not _lib.lib().b200dp_adj3_applicable(B, N, M):
             return None
-        _check_in("E", E, (B, N2, M2))
+        if E is not None:
+            _check_in("E", E, (B, N2, M2))
         if Ztheta is None:
             zt = torch.zeros((B, N, M), dtype=torch.float32, device=Q.device)
         elif interior:
@@ -266,8 +274,7 @@ def _sq_flags(plan, flags, fwd):
 def _sq_ws(plan, t):
     from . import plan as _plan
     stream = _stream(t)
-    ws, epoch = _plan.workspace(t.device, stream, plan.ws_bytes)
-    return ws, epoch, stream
+    return _plan.workspace(t.device, stream, plan.ws_bytes), stream
 
 
 def _sq_check_operand(name, t, plan):
@@ -320,8 +327,8 @@ def sq_forward(plan, theta, A, mode="nw", need_q=True, flags=0):
         Q = torch.empty(plan.q_floats, dtype=torch.float32, device=theta.device) if need_q else None
         alloc = torch.zeros if plan.has_empty else torch.empty      # an empty pair scores 0 (nothing to sum)
         Vt = alloc(plan.B, dtype=torch.float32, device=theta.device)
-        ws, epoch, stream = _sq_ws(plan, theta)
-        rc = _lib.lib().b200dp_sq_fwd(_ptr(plan.fwd_tab), plan.nstrips, _ptr(ws), epoch, _ptr(theta), _ptr(A),
+        ws, stream = _sq_ws(plan, theta)
+        rc = _lib.lib().b200dp_sq_fwd(_ptr(plan.fwd_tab), plan.nstrips, _ptr(ws), _ptr(theta), _ptr(A),
                                       _ptr(Q), _ptr(Vt), MODES[mode], _sq_flags(plan, flags, True), stream)
         _lib.check(rc, "b200dp_sq_fwd")
     return Vt, Q
@@ -344,8 +351,8 @@ def sq_backward(plan, Et, Q, mode="nw", flags=0):
     Et = Et.detach()
     with torch.cuda.device(Q.device):
         E = _sq_out_like(plan, Q)
-        ws, epoch, stream = _sq_ws(plan, Q)
-        rc = _lib.lib().b200dp_sq_bwd(_ptr(plan.bwd_tab), plan.nstrips, _ptr(ws), epoch, _ptr(Et),
+        ws, stream = _sq_ws(plan, Q)
+        rc = _lib.lib().b200dp_sq_bwd(_ptr(plan.bwd_tab), plan.nstrips, _ptr(ws), _ptr(Et),
                                       Et.stride(0) if plan.B > 0 else 0, _ptr(Q), _ptr(E), MODES[mode],
                                       _sq_flags(plan, flags, False), stream)
         _lib.check(rc, "b200dp_sq_bwd")
@@ -367,8 +374,8 @@ def sq_adjoint_forward(plan, Q, Zt, ZA=None, E=None, flags=0):
         QdE = torch.empty(plan.q_floats, dtype=torch.float32, device=Q.device)
         alloc = torch.zeros if plan.has_empty else torch.empty
         Vtd = alloc(plan.B, dtype=torch.float32, device=Q.device)
-        ws, epoch, stream = _sq_ws(plan, Q)
-        rc = _lib.lib().b200dp_sq_adj_fwd(_ptr(plan.fwd_tab), plan.nstrips, _ptr(ws), epoch, _ptr(Q), _ptr(Zt),
+        ws, stream = _sq_ws(plan, Q)
+        rc = _lib.lib().b200dp_sq_adj_fwd(_ptr(plan.fwd_tab), plan.nstrips, _ptr(ws), _ptr(Q), _ptr(Zt),
                                           _ptr(ZA), _ptr(E), _ptr(Vtd), _ptr(QdE), _sq_flags(plan, flags, True), stream)
         _lib.check(rc, "b200dp_sq_adj_fwd")
     return Vtd, QdE
@@ -379,8 +386,8 @@ def sq_adjoint_backward(plan, Q, QdE, flags=0):
     reference's padded Ed, nw.py:270-312, 386)."""
     with torch.cuda.device(Q.device):
         Ed = _sq_out_like(plan, Q)
-        ws, epoch, stream = _sq_ws(plan, Q)
-        rc = _lib.lib().b200dp_sq_adj_bwd(_ptr(plan.bwd_tab), plan.nstrips, _ptr(ws), epoch, _ptr(Q), _ptr(QdE),
+        ws, stream = _sq_ws(plan, Q)
+        rc = _lib.lib().b200dp_sq_adj_bwd(_ptr(plan.bwd_tab), plan.nstrips, _ptr(ws), _ptr(Q), _ptr(QdE),
                                           _ptr(Ed), _sq_flags(plan, flags, False), stream)
         _lib.check(rc, "b200dp_sq_adj_bwd")
     return Ed

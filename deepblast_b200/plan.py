@@ -164,20 +164,20 @@ def packed_plan(xlen, ylen, device=None):
     return get_plan(len(xl), max(1, int(xl.max(initial=1))), max(1, int(yl.max(initial=1))), xl, yl, True, device)
 
 
-# ---- per-(device, stream) workspace: zeroed once, self-cleaning, one launch at a time -------
+# ---- per-(device, stream) workspace: zeroed once, self-cleaning, one launch at a time ---------
 _ws = {}
 _ws_lock = threading.Lock()
 
 
 def workspace(device, stream_ptr, nbytes):
-    """(tensor, epoch) for the next strip-queue launch on this stream."""
+    """The workspace tensor for strip-queue launches on this stream (grown when a plan needs more;
+    a fresh one is zero-filled on the current stream, which is all the kernels require)."""
     key = (device.index, int(stream_ptr))
     with _ws_lock:
-        ent = _ws.get(key)
-        if ent is None or ent[0].numel() < nbytes:
+        ws = _ws.get(key)
+        if ws is None or ws.numel() < nbytes:
             size = max(int(nbytes), 1 << 20)
-            size = (size * 5 // 4 + 255) & ~255 if ent is not None else (size + 255) & ~255
-            ent = [torch.zeros(size, dtype=torch.uint8, device=device), ent[1] if ent is not None else 0]
-            _ws[key] = ent
-        ent[1] = ent[1] % 0xFFFFFFF0 + 1          # never 0
-        return ent[0], ent[1]
+            if ws is not None:
+                size = size * 5 // 4
+            ws = _ws[key] = torch.zeros((size + 255) & ~255, dtype=torch.uint8, device=device)
+        return ws

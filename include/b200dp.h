@@ -50,9 +50,11 @@ extern "C" {
 #define B200DP_MODE_NW 0
 #define B200DP_MODE_SW 1
 
-/* flags */
+/* flags (the library reads no environment variables: every dispatch override is a flag) */
+#define B200DP_NO_CHAINED    0x1   /* never the chained kernels (large equal-size batches then take the hand-off kernels) */
 #define B200DP_NO_TMA        0x2   /* stage tiles with cp.async instead of TMA (debug / unaligned) */
 #define B200DP_V1_KERNELS    0x4   /* use the general kernels even where the fast path applies */
+#define B200DP_FORCE_CHAINED 0x8   /* the chained kernels at any batch size (tests) */
 #define B200DP_WARPS_SHIFT   4     /* bits 4..7: warps per pair (1,2,4,8); 0 = choose automatically */
 #define B200DP_CTAS_SHIFT    8     /* bits 8..23: grid size override; 0 = choose automatically */
 
@@ -182,10 +184,11 @@ int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h
  * strip not before its predecessor is far enough ahead); <= 0 picks a default.
  *
  * The launchers take a DEVICE workspace of b200dp_sq_workspace_bytes(info.bnd_words) bytes,
- * zero-filled ONCE when allocated (the kernels leave it clean) and used by one launch at a time
- * (launches on one stream are fine), and an `epoch` that differs from launch to launch on the
- * same workspace and is never 0.  flags: B200DP_CTAS_SHIFT (grid override), B200DP_SQ_RING_SHIFT. */
-#define B200DP_SQ_RING_SHIFT 24    /* bits 24..27: tile ring depth override; 0 = default */
+ * zero-filled ONCE when allocated and used by one launch at a time (launches on one stream are
+ * fine): the kernels leave the ticket counter clean and count the launches in the workspace
+ * itself (the tag that tells this launch's hand-off words from stale ones), so launches may be
+ * captured in CUDA graphs and replayed.  flags: B200DP_CTAS_SHIFT (grid override), B200DP_SQ_RING_SHIFT. */
+#define B200DP_SQ_RING_SHIFT 24    /* bits 24..27: tile ring depth override (all fast kernels); 0 = default */
 #define B200DP_SQ_DBG_SHIFT  28    /* bits 28..30: diagnostics (timing experiments; results are wrong when set) */
 
 typedef struct b200dp_plan_info {
@@ -212,20 +215,20 @@ void b200dp_sq_set_trace(void* trace);
 
 /* _forward_pass_kernel (nw_cuda.py:46-79).  Q = NULL: score only, Vt alone
  * (deepblast/alignment.py:127-137 calls ddp(theta, A) under no_grad). */
-int b200dp_sq_fwd(const void* fwd_tab, int nstrips, void* workspace, unsigned epoch,
+int b200dp_sq_fwd(const void* fwd_tab, int nstrips, void* workspace,
                   const float* theta, const float* A, float* Q, float* Vt, int mode, int flags,
                   void* stream);
 /* _backward_pass_kernel (nw_cuda.py:82-102): Et, Q -> E (interior layout). */
-int b200dp_sq_bwd(const void* bwd_tab, int nstrips, void* workspace, unsigned epoch,
+int b200dp_sq_bwd(const void* bwd_tab, int nstrips, void* workspace,
                   const float* Et, long long et_stride, const float* Q, float* E, int mode,
                   int flags, void* stream);
 /* _adjoint_forward_pass_kernel (nw_cuda.py:105-139): Q, Zt (interior layout), ZA or NULL, E
  * (interior layout) or NULL -> Vtd, QdE = Qd * E (Qd itself when E is NULL). */
-int b200dp_sq_adj_fwd(const void* fwd_tab, int nstrips, void* workspace, unsigned epoch,
+int b200dp_sq_adj_fwd(const void* fwd_tab, int nstrips, void* workspace,
                       const float* Q, const float* Zt, const float* ZA, const float* E,
                       float* Vtd, float* QdE, int flags, void* stream);
 /* _adjoint_backward_pass_kernel (nw_cuda.py:142-165): Q, QdE -> Ed (interior layout). */
-int b200dp_sq_adj_bwd(const void* bwd_tab, int nstrips, void* workspace, unsigned epoch,
+int b200dp_sq_adj_bwd(const void* bwd_tab, int nstrips, void* workspace,
                       const float* Q, const float* QdE, float* Ed, int flags, void* stream);
 
 #ifdef __cplusplus

@@ -91,8 +91,9 @@ SHAPES = [(2, 1, 1), (2, 1, 9), (2, 9, 1), (3, 31, 33), (2, 32, 32), (2, 64, 64)
           (2, 96, 200), (1, 256, 193), (2, 256, 256), (1, 300, 77), (1, 130, 520)]
 
 
-def check_fwd_bwd(ops, theta, A, Et, mode, flags):
+def check_fwd_bwd(ops, theta, A, Et, mode, flags, flags_bwd=None):
     """Forward + backward against the oracle."""
+    flags_bwd = flags if flags_bwd is None else flags_bwd
     N = theta.shape[1]
     Vt_o, Q_o = O.forward_pass(theta.numpy(), A.numpy(), mode)
     E_o = O.backward_pass(Et.numpy(), Q_o, mode)
@@ -100,7 +101,7 @@ def check_fwd_bwd(ops, theta, A, Et, mode, flags):
     Vt, Q = ops.forward_pass(th, a, mode, flags=flags)
     np.testing.assert_allclose(Vt.cpu().numpy(), Vt_o, rtol=1e-6)
     np.testing.assert_allclose(ops.q_to_reference(Q, N).cpu().numpy(), Q_o, rtol=0, atol=ATOL_QE)
-    E = ops.backward_pass(Et.to(dev()), Q, mode, flags=flags, N=N)
+    E = ops.backward_pass(Et.to(dev()), Q, mode, flags=flags_bwd, N=N)
     np.testing.assert_allclose(E.cpu().numpy(), E_o, rtol=0, atol=ATOL_QE * 2)
 
 
@@ -224,16 +225,13 @@ CHAINED = [
 
 
 @pytest.mark.parametrize("mode,B,N,M,nch,ctas,ring,bring", CHAINED)
-def test_chained_kernels_vs_oracle(ops, monkeypatch, mode, B, N, M, nch, ctas, ring, bring):
-    """softdp_fwd3 / softdp_bwd3 (the large-batch path) forced onto small batches."""
-    monkeypatch.setenv("B200DP_V3MIN", "1")
-    monkeypatch.setenv("B200DP_NCH", str(nch))
-    monkeypatch.setenv("B200DP_RING", str(ring))
-    monkeypatch.setenv("B200DP_BRING", str(bring))
-    if ctas:
-        monkeypatch.setenv("B200DP_CTAS", str(ctas))
+def test_chained_kernels_vs_oracle(ops, mode, B, N, M, nch, ctas, ring, bring):
+    """softdp_fwd3 / softdp_bwd3 (the large-batch path) forced onto small batches (flags:
+    FORCE_CHAINED, ring depth, grid size)."""
+    fl = ops.FORCE_CHAINED | (ctas << ops.CTAS_SHIFT)
     theta, A = rand_inputs(B, N, M, seed=7)
-    check_fwd_bwd(ops, theta, A, torch.linspace(0.5, 1.5, B), mode, 0)
+    check_fwd_bwd(ops, theta, A, torch.linspace(0.5, 1.5, B), mode, fl | (ring << ops.SQ_RING_SHIFT),
+                  fl | (bring << ops.SQ_RING_SHIFT))
 
 
 @pytest.mark.parametrize("mode", ["nw", "sw"])
@@ -426,12 +424,10 @@ ADJ3 = [
 
 
 @pytest.mark.parametrize("mode,B,N,M,ctas,with_za", ADJ3)
-def test_chained_adjoint_pair_vs_oracle(ops, monkeypatch, mode, B, N, M, ctas, with_za):
+def test_chained_adjoint_pair_vs_oracle(ops, mode, B, N, M, ctas, with_za):
     """The chained adjoint sweeps (softdp_fwd3 / softdp_bwd3 with ADJ, forced onto small
     batches) against the oracle's nw.py:178-199 / 251-267, from the engine's own Q and E."""
-    monkeypatch.setenv("B200DP_V3MIN", "1")
-    if ctas:
-        monkeypatch.setenv("B200DP_CTAS", str(ctas))
+    fl = ops.FORCE_CHAINED | (ctas << ops.CTAS_SHIFT)
     theta, A = rand_inputs(B, N, M, seed=11)
     Et = torch.linspace(0.5, 1.5, B)
     g = torch.Generator().manual_seed(12)
@@ -441,17 +437,16 @@ def test_chained_adjoint_pair_vs_oracle(ops, monkeypatch, mode, B, N, M, ctas, w
     E_o = O.backward_pass(Et.numpy(), Q_o, mode)
     Vtd_o, Qd_o = O.adjoint_forward_pass(Q_o, Zt.numpy(), ZA.numpy() if with_za else np.zeros((B, N, M), np.float32))
     Ed_o = O.adjoint_backward_pass(E_o, Q_o, Qd_o)
-    Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), mode)
-    E = ops.backward_pass(Et.to(dev()), Q, mode, N=N)
-    res = ops.adjoint_pair_fast(Q, E, Zt.to(dev()), ZA.to(dev()) if with_za else None)
+    Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), mode, flags=fl)
+    E = ops.backward_pass(Et.to(dev()), Q, mode, N=N, flags=fl)
+    res = ops.adjoint_pair_fast(Q, E, Zt.to(dev()), ZA.to(dev()) if with_za else None, flags=fl)
     assert res is not None
     Vtd, Ed = res
     scale = float(np.abs(Vtd_o).max()) + 1.0
     np.testing.assert_allclose(Vtd.cpu().numpy(), Vtd_o, rtol=0, atol=2e-5 * scale)
     np.testing.assert_allclose(Ed.cpu().numpy(), Ed_o, rtol=0, atol=1e-4 * max(1.0, float(np.abs(Ed_o).max())))
     # and the same answer as the general kernels on the same inputs
-    monkeypatch.setenv("B200DP_V3", "0")
-    assert ops.adjoint_pair_fast(Q, E, Zt.to(dev()), None) is None
+    assert ops.adjoint_pair_fast(Q, E, Zt.to(dev()), None, flags=ops.NO_CHAINED) is None
     Vtd2, Qd2 = ops.adjoint_forward_pass(Q, Zt.to(dev()), ZA.to(dev()) if with_za else torch.zeros(B, N, M, device=dev()))
     Ed2 = ops.adjoint_backward_pass(E, Q, Qd2)
     np.testing.assert_allclose(Vtd.cpu().numpy(), Vtd2.cpu().numpy(), rtol=0, atol=2e-5 * scale)
