@@ -231,6 +231,19 @@ int b200dp_sq_adj_fwd(const void* fwd_tab, int nstrips, void* workspace,
 int b200dp_sq_adj_bwd(const void* bwd_tab, int nstrips, void* workspace,
                       const float* Q, const float* QdE, float* Ed, int flags, void* stream);
 
+/* ---- the step before the DP: theta = softplus(zx zy^T), A = logsigmoid(gx gy^T)
+ * (deepblast/alignment.py:122-123,134-135,162-163) as one batched tcgen05 GEMM launch with the
+ * activation fused into the epilogue (softdp_gemm.cu).  zx, gx [B, Lx, D], zy, gy [B, Ly, D] fp32
+ * contiguous, D % 64 == 0; fp32 accuracy through a bf16 hi/lo split (three tensor-core passes).
+ * Outputs in the DP's operand layout: pair_off == NULL: dense [B, Lx, Ly]; else pair b at element
+ * offset pair_off[b] with pitch (m_b + 3) & ~3 (b200dp_plan_build, packed).  xlen / ylen (device
+ * int32[B], nullable): only the n_b x m_b corner of pair b is computed and written.
+ * workspace: DEVICE memory, b200dp_theta_a_workspace() bytes (the bf16 copies of the embeddings). */
+size_t b200dp_theta_a_workspace(int B, int Lx, int Ly, int D);
+int b200dp_theta_a(const float* zx, const float* zy, const float* gx, const float* gy, int B, int Lx,
+                   int Ly, int D, const int32_t* xlen, const int32_t* ylen, const long long* pair_off,
+                   float* theta, float* A, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
