@@ -155,7 +155,10 @@ def make_classes(mode, prefix):
                 return E, A, None, None, None, None
             if ctx.lens != (None, None):
                 Q._b200dp_lens = ctx.lens
-            E, A = FunctionBackward.apply(theta, A, Et, Q, operator, True, torch.is_grad_enabled())
+            # a second copy of E's interior only when a double backward can follow AND reach theta
+            # (create_graph with a differentiable Et or theta); plain inference never pays for it
+            keep = torch.is_grad_enabled() and (Et.requires_grad or theta.requires_grad)
+            E, A = FunctionBackward.apply(theta, A, Et, Q, operator, True, keep)
             return E, A, None, None, None, None
 
     class Decoder(nn.Module):

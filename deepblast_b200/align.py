@@ -32,9 +32,11 @@ def traceback_pairs(decoder, match, gap, xlen, ylen, variant="cuda"):
     match, gap : CUDA fp32 [B, N, M] (theta and A of alignment.py:162-163)
     xlen, ylen : per-pair lengths (tensor, list or array of B ints)
     """
-    B = match.shape[0]
-    xl = torch.as_tensor(xlen, dtype=torch.int32).reshape(B)
-    yl = torch.as_tensor(ylen, dtype=torch.int32).reshape(B)
+    B, N, M = match.shape
+    xl = torch.as_tensor(xlen, dtype=torch.int32).reshape(B).cpu()
+    yl = torch.as_tensor(ylen, dtype=torch.int32).reshape(B).cpu()
+    if int(xl.min()) < 1 or int(yl.min()) < 1 or int(xl.max()) > N or int(yl.max()) > M:
+        raise ValueError(f"lengths must satisfy 1 <= xlen <= {N}, 1 <= ylen <= {M}")
     with torch.enable_grad():
         th = match if match.requires_grad else match.detach().requires_grad_()
         a = gap if gap.requires_grad else gap.detach().requires_grad_()

@@ -787,12 +787,20 @@ int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h
         cudaError_t e_ = (call);                                   \
         if (e_ != cudaSuccess) return cuda_fail(e_, what);         \
     } while (0)
+    // The enqueue sequence runs inside a lambda so that an error in the middle still reaches the join
+    // below: work already queued on the internal streams keeps using the workspace and the host
+    // buffers, and the caller's stream must not run past it (the Python side may drop its
+    // references as soon as this function returns an error).
+    auto enqueue = [&]() -> int {
     // fork: everything below is ordered after the work already queued on the caller's stream
     B200DP_CK(cudaEventRecord(hp.fork, user), "b200dp_decode_host: fork");
     B200DP_CK(cudaStreamWaitEvent(hp.s_in, hp.fork, 0), "b200dp_decode_host: fork");
     B200DP_CK(cudaStreamWaitEvent(hp.s_cmp, hp.fork, 0), "b200dp_decode_host: fork");
     B200DP_CK(cudaStreamWaitEvent(hp.s_out, hp.fork, 0), "b200dp_decode_host: fork");
-    if (!Et_h) fill_one_kernel<<<1, 1, 0, hp.s_cmp>>>(one);
+    if (!Et_h) {
+        fill_one_kernel<<<1, 1, 0, hp.s_cmp>>>(one);
+        B200DP_CK(cudaGetLastError(), "b200dp_decode_host: fill launch");
+    }
     int c = 0;
     for (int b0 = 0; b0 < B; b0 += chunk_pairs, ++c) {
         const int nb = (B - b0 < chunk_pairs) ? (B - b0) : chunk_pairs;
@@ -830,10 +838,19 @@ int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h
                   "b200dp_decode_host: D2H Vt");
         B200DP_CK(cudaEventRecord(hp.out_done[sl], hp.s_out), "b200dp_decode_host: record");
     }
-    // join: the caller's stream continues after the last download (s_out runs in order, and
-    // every download waited for its sweeps, which waited for their uploads)
-    B200DP_CK(cudaEventRecord(hp.join, hp.s_out), "b200dp_decode_host: join");
-    B200DP_CK(cudaStreamWaitEvent(user, hp.join, 0), "b200dp_decode_host: join");
+    return 0;
+    };
+    const int rc = enqueue();
+    // join: the caller's stream continues after the last download (s_out runs in order, and every
+    // download waited for its sweeps, which waited for their uploads); after an error all three
+    // internal streams are joined, whatever they got to
+    cudaStream_t tojoin[3] = {hp.s_out, hp.s_cmp, hp.s_in};
+    for (int i = 0; i < (rc ? 3 : 1); ++i) {
+        cudaError_t e1 = cudaEventRecord(hp.join, tojoin[i]);
+        if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(user, hp.join, 0);
+        if (e1 != cudaSuccess && !rc) return cuda_fail(e1, "b200dp_decode_host: join");
+    }
+    if (rc) return rc;
 #undef B200DP_CK
     return 0;
 }

@@ -250,8 +250,10 @@ struct PairDims {
 };
 
 __device__ __forceinline__ void strip_load_pair(Strip& s, const PairDims& d) {
-    s.n = d.xlen ? d.xlen[s.pair] : d.N;
-    s.m = d.ylen ? d.ylen[s.pair] : d.M;
+    // lengths are clamped to the tensor like the reference's slices theta[b, :n, :m]
+    // (deepblast/alignment.py:166-169): an over-long length must not run past the pair's storage
+    s.n = d.xlen ? min(max(d.xlen[s.pair], 0), d.N) : d.N;
+    s.m = d.ylen ? min(max(d.ylen[s.pair], 0), d.M) : d.M;
     s.K = (s.n > 0 && s.m > 0) ? ((s.n + kTile - 1) / kTile) : 0;
 }
 __device__ __forceinline__ void strip_seek(Strip& s, const PairDims& d, int w, int W) {

@@ -24,8 +24,9 @@ __device__ __forceinline__ int tb_wrap(int idx, int n) { return idx < 0 ? idx + 
 __global__ void softdp_traceback_kernel(TracebackParams p) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= p.B) return;
-    const int n = p.xlen ? p.xlen[b] : p.N;
-    const int m = p.ylen ? p.ylen[b] : p.M;
+    // clamped like the reference's slice aln[b, :n, :m] (alignment.py:166-170): never past the tensor
+    const int n = p.xlen ? min(max(p.xlen[b], 0), p.N) : p.N;
+    const int m = p.ylen ? min(max(p.ylen[b], 0), p.M) : p.M;
     const float* g = p.grad + (long long)b * p.sb;
     int32_t* out = p.out + (long long)b * p.cap * 3;
     // sentinels of nw.py:418 / nw_cuda.py:291, compared after rounding to fp32

@@ -135,7 +135,8 @@ def forward_pass(theta, A, mode="nw", xlen=None, ylen=None, flags=0):
     xlen, ylen = _lens(xlen, ylen, B, N, M, theta.device)
     with torch.cuda.device(theta.device):
         Q = q_empty(B, N, M, theta.device)
-        Vt = torch.empty(B, dtype=torch.float32, device=theta.device)
+        # (with lengths an empty pair has no strips: its score stays 0, nothing to sum)
+        Vt = (torch.zeros if xlen is not None else torch.empty)(B, dtype=torch.float32, device=theta.device)
         rc = _lib.lib().b200dp_fwd(_ptr(theta), _ptr(A), _ptr(Q), _ptr(Vt), _ptr(xlen), _ptr(ylen),
                                    B, N, M, MODES[mode], flags, _stream(theta))
         _lib.check(rc, "b200dp_fwd")
@@ -453,7 +454,10 @@ def decode_host(theta_h, A_h, mode="nw", Et_h=None, chunk_pairs=None, out=None, 
 
 def decode_host_async(theta_h, A_h, mode="nw", Et_h=None, chunk_pairs=None, out=None, device=None, flags=0):
     """Enqueue only; returns (Vt_h, E_h padded [B,N+2,M+2]) pinned buffers that are valid
-    after the current stream of `device` has been synchronised."""
+    after the current stream of `device` has been synchronised.  The copies are asynchronous: the
+    CALLER keeps theta_h, A_h, Et_h and `out` alive and unmodified until that synchronisation
+    (freeing pinned tensors earlier lets torch's pinned allocator hand the memory out again while
+    the DMA is still in flight)."""
     for name, t in (("theta_h", theta_h), ("A_h", A_h)):
         if t.is_cuda:
             raise RuntimeError(f"{name} must be a host tensor (use Decoder.decode for CUDA tensors)")
@@ -467,7 +471,14 @@ def decode_host_async(theta_h, A_h, mode="nw", Et_h=None, chunk_pairs=None, out=
     theta_h = theta_h.contiguous()
     A_h = A_h.contiguous()
     if Et_h is not None:
+        if Et_h.is_cuda or tuple(Et_h.shape) != (B,):
+            raise RuntimeError("Et_h must be a host tensor of shape [B]")
         Et_h = Et_h.contiguous().float()
+    if out is not None:
+        # the C side copies B and B * (N+2) * (M+2) floats into these buffers: check before it does
+        for name, t, shape in (("out[0] (Vt_h)", out[0], (B,)), ("out[1] (E_h)", out[1], (B, N + 2, M + 2))):
+            if t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != shape or not t.is_contiguous():
+                raise RuntimeError(f"{name} must be a contiguous float32 host tensor of shape {shape}")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     if chunk_pairs is None:
         # enough chunks to hide the first upload and the last download, each still a few MB

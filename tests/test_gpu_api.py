@@ -7,6 +7,8 @@ import torch
 from torch.autograd import gradcheck
 from torch.autograd.gradcheck import gradgradcheck
 
+from oracle import softdp as O
+
 pytestmark = pytest.mark.gpu
 
 CASES = ["t_nw_cuda_5x5", "r8x8", "r17x23", "r33x40", "r64x48"]
@@ -277,3 +279,79 @@ def test_matrix_cross_entropy_on_decode_output():
     g2, = torch.autograd.grad(ref, theta)
     scale = float(g2.abs().max())
     np.testing.assert_allclose(g1.cpu().numpy(), g2.cpu().numpy(), rtol=0, atol=2e-4 * scale)
+
+
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+def test_replay_of_neuralaligner_call_pattern(mode):
+    """What deepblast.alignment.NeuralAligner does with the decoder, call for call:
+    forward (alignment.py:117-124): ddp.decode(theta, A) on the padded batch;
+    score (alignment.py:127-137): ddp(theta, A) under no_grad;
+    traceback (alignment.py:160-171): per pair, decode on the NON-CONTIGUOUS B = 1 slices
+    match[b, :xlen[b], :ylen[b]].unsqueeze(0) and ddp.traceback(aln.squeeze())."""
+    dec = decoders()[mode]('softmax')
+    B, L = 4, 70
+    g = torch.Generator().manual_seed(17)
+    match = torch.nn.functional.softplus(torch.randn(B, L, L, generator=g)).to(dev())
+    gap = torch.nn.functional.logsigmoid(torch.randn(B, L, L, generator=g)).to(dev())
+    xlen, ylen = [70, 33, 52, 9], [70, 41, 64, 70]
+    # forward
+    theta, A = match.clone().requires_grad_(), gap.clone().requires_grad_()
+    aln = dec.decode(theta, A)
+    assert aln.shape == (B, L, L)
+    Vt_o, Q_o = O.forward_pass(match.cpu().numpy(), gap.cpu().numpy(), mode)
+    E_o = O.backward_pass(np.ones(B, np.float32), Q_o, mode)
+    np.testing.assert_allclose(aln.detach().cpu().numpy(), E_o[:, 1:-1, 1:-1], rtol=0, atol=2e-5)
+    # score
+    with torch.no_grad():
+        ascore = dec(match, gap)
+    np.testing.assert_allclose(ascore.cpu().numpy(), Vt_o, rtol=1e-6)
+    # traceback generator
+    for b in range(B):
+        m_b = match[b, :xlen[b], :ylen[b]].unsqueeze(0)
+        g_b = gap[b, :xlen[b], :ylen[b]].unsqueeze(0)
+        assert not m_b.is_contiguous() or ylen[b] == L      # a row slice of full rows is still contiguous
+        aln_b = dec.decode(m_b.requires_grad_(), g_b.requires_grad_())
+        decoded = dec.traceback(aln_b.squeeze())
+        _, Qb = O.forward_pass(m_b.detach().cpu().numpy(), g_b.detach().cpu().numpy(), mode)
+        Eb = O.backward_pass(np.ones(1, np.float32), Qb, mode)[0, 1:-1, 1:-1]
+        np.testing.assert_allclose(aln_b.detach().cpu().numpy()[0], Eb, rtol=0, atol=2e-5)
+        # the walk itself is bit-exact on identical input
+        assert decoded == O.traceback(aln_b.detach().cpu().numpy()[0], "cuda")
+
+
+@pytest.mark.parametrize("N,M", [(33, 2047), (2047, 40)])
+def test_lattice_at_the_reference_column_limit(N, M):
+    """max_cols = 2048 in the reference's kernels (nw_cuda.py:11) means M <= 2047; same here."""
+    from deepblast_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    theta = torch.rand(1, N, M, generator=g)
+    A = -torch.rand(1, N, M, generator=g)
+    Vt_o, Q_o = O.forward_pass(theta.numpy(), A.numpy(), "nw")
+    E_o = O.backward_pass(np.ones(1, np.float32), Q_o, "nw")
+    Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), "nw")
+    E = ops.backward_pass(torch.ones(1, device=dev()), Q, "nw", N=N)
+    np.testing.assert_allclose(Vt.cpu().numpy(), Vt_o, rtol=1e-6)
+    np.testing.assert_allclose(E.cpu().numpy(), E_o, rtol=0, atol=2e-5)
+
+
+def test_overlong_and_empty_lengths_are_clamped_like_the_reference_slices():
+    """xlen > N clamps (the reference slices theta[b, :xlen[b]], alignment.py:166), xlen <= 0 gives an
+    empty pair with score 0 -- on the round-1 kernels (M % 4 != 0 keeps the batch off the strip-queue path)."""
+    from deepblast_b200 import ops
+    B, N, M = 3, 40, 37
+    g = torch.Generator().manual_seed(8)
+    theta = torch.rand(B, N, M, generator=g)
+    A = -torch.rand(B, N, M, generator=g)
+    xl = torch.tensor([500, 0, 17], dtype=torch.int32)
+    yl = torch.tensor([37, 20, 900], dtype=torch.int32)
+    Vt, Q = ops.forward_pass(theta.to(dev()), A.to(dev()), "nw", xl.to(dev()), yl.to(dev()))
+    E = ops.backward_pass(torch.ones(B, device=dev()), Q, "nw", xl.to(dev()), yl.to(dev()), N=N)
+    torch.cuda.synchronize()
+    for b, (n, m) in enumerate([(40, 37), (0, 0), (17, 37)]):
+        if n == 0:
+            assert float(Vt[b]) == 0.0
+            continue
+        Vt_o, Q_o = O.forward_pass(theta[b:b + 1, :n, :m].numpy(), A[b:b + 1, :n, :m].numpy(), "nw")
+        E_o = O.backward_pass(np.ones(1, np.float32), Q_o, "nw")
+        np.testing.assert_allclose(float(Vt[b]), Vt_o[0], rtol=1e-6)
+        np.testing.assert_allclose(E[b, 1:n + 1, 1:m + 1].cpu().numpy(), E_o[0, 1:-1, 1:-1], rtol=0, atol=2e-5)

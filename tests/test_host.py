@@ -247,3 +247,98 @@ def test_header_is_plain_c_and_bindings_match_it(tmp_path):
         args = args.strip()
         n = 0 if args in ("", "void") else len(args.split(","))
         assert n == len(_lib.EXPORTS[name][1]), (name, n, len(_lib.EXPORTS[name][1]))
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "deepblast")), reason="reference checkout not present")
+def test_install_on_the_real_reference_alignment_module():
+    """The real caller: deepblast.alignment (imported from the reference checkout with a stub `Bio`,
+    SURVEY.md section 8c) picks up our decoders through install() -- NeuralAligner(device='cuda').ddp
+    is ours for both alignment modes (alignment.py:67-79) -- and install() leaves autograd's anomaly
+    mode as it found it (importing deepblast.nw_cuda switches it on, nw_cuda.py:9).  Runs in a
+    subprocess so that the reference modules do not leak into the other tests."""
+    code = r"""
+import sys, types
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+bio = types.ModuleType("Bio"); seqio = types.ModuleType("Bio.SeqIO"); bio.SeqIO = seqio
+sys.modules["Bio"] = bio; sys.modules["Bio.SeqIO"] = seqio
+import torch
+assert not torch.is_anomaly_enabled()
+import deepblast_b200
+patched = deepblast_b200.install()
+assert not torch.is_anomaly_enabled(), "install() left anomaly mode on"
+assert "deepblast.nw_cuda.NeedlemanWunschDecoder" in patched and "deepblast.sw_cuda.SmithWatermanDecoder" in patched
+from deepblast.alignment import NeuralAligner            # binds NWDecoderCUDA / SWDecoderCUDA at import
+nw = NeuralAligner(22, 16, 16, 16, n_layers=1, device='cuda')
+sw = NeuralAligner(22, 16, 16, 16, n_layers=1, device='cuda', alignment_mode='smith-waterman')
+assert type(nw.ddp).__module__ == "deepblast_b200.nw_cuda", type(nw.ddp)
+assert type(sw.ddp).__module__ == "deepblast_b200.sw_cuda", type(sw.ddp)
+assert nw.ddp.operator == 'softmax'
+# the other order: alignment imported first, install() afterwards
+import deepblast.alignment as ali
+ali.NWDecoderCUDA = None
+deepblast_b200.install()
+assert ali.NWDecoderCUDA is deepblast_b200.nw_cuda.NeedlemanWunschDecoder
+torch.autograd.set_detect_anomaly(True)
+deepblast_b200.install()
+assert torch.is_anomaly_enabled(), "install() must not switch a caller's anomaly mode off either"
+print("ok")
+""" % (ROOT, REFERENCE)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_plan_builder_orders_every_strip_after_its_dependency():
+    """b200dp_plan_build (host code of the C ABI, no GPU): every strip of both tables comes after the
+    strip it depends on, offsets do not overlap, lengths are clamped, empty pairs have no strips."""
+    from deepblast_b200 import plan
+    rec = np.dtype([('t_off', '<i8'), ('q_off', '<i8'), ('b_in', '<i8'), ('b_out', '<i8'), ('rows', '<i4'), ('m', '<i4'),
+                    ('pitch', '<i4'), ('pair', '<i4'), ('flags', '<i4'), ('k', '<i4'), ('pad', '<i4', 2)])
+    rng = np.random.default_rng(3)
+    B, N, M = 40, 300, 260
+    xl = rng.integers(-5, 340, B)
+    yl = rng.integers(-5, 300, B)
+    for packed in (False, True):
+        if not packed:
+            p = plan.Plan(B, N, M, xl, yl, packed=False, device="cpu", resident_warps=(37, 11))
+        else:
+            p = plan.Plan(B, N, M, xl, yl, packed=True, device="cpu", resident_warps=(37, 11))
+        n = np.clip(xl, 0, N); m = np.clip(yl, 0, M)
+        n[(n == 0) | (m == 0)] = 0
+        K = (n + 31) // 32
+        assert p.nstrips == int(K.sum()) and p.cells == int((n.astype(np.int64) * np.where(n > 0, m, 0)).sum())
+        for d, tab in enumerate(p.tabs_host):
+            t = tab.view(rec).reshape(-1)[:p.nstrips]
+            seen = set()
+            for r in t:
+                b, k = int(r['pair']), int(r['k'])
+                dep = k - 1 if d == 0 else k + 1
+                if 0 <= dep < K[b]:
+                    assert (b, dep) in seen, (d, b, k)
+                assert (b, k) not in seen
+                seen.add((b, k))
+                assert r['rows'] == min(32, n[b] - 32 * k) and r['m'] == m[b]
+                assert (r['b_in'] >= 0) == (0 <= dep < K[b])
+            assert len(seen) == p.nstrips
+        # packed operands: pair blocks do not overlap and fit
+        if packed:
+            ends = p.pair_off[:B] + n.astype(np.int64) * p.pitch
+            order = np.argsort(p.pair_off[:B], kind="stable")
+            assert np.all(p.pair_off[:B][order][1:] >= ends[order][:-1]) and int(ends.max()) <= p.packed_floats
+
+
+def test_packed_layout_round_trip_on_cpu():
+    from deepblast_b200 import plan
+    B, N, M = 5, 40, 37
+    xl, yl = [40, 3, 17, 0, 25], [37, 37, 5, 9, 36]
+    p = plan.Plan(B, N, M, xl, yl, packed=True, device="cpu")
+    g = torch.Generator().manual_seed(0)
+    dense = torch.rand(B, N, M, generator=g)
+    flat = p.pack(dense)
+    back = p.unpack(flat)
+    for b in range(B):
+        n, m = int(p.xlen[b]), int(p.ylen[b])
+        assert torch.equal(back[b, :n, :m], dense[b, :n, :m])
+        assert float(back[b, n:].abs().sum()) == 0 and float(back[b, :, m:].abs().sum()) == 0
