@@ -670,7 +670,11 @@ int b200dp_mxent_fwd(const float* Ytrue, const float* Ypred, long long pb, long 
     cudaError_t e0 = cudaMemsetAsync(pair_loss, 0, (size_t)B * 4, st);
     if (e0 == cudaSuccess) e0 = cudaMemsetAsync(pair_count, 0, (size_t)B * 4, st);
     if (e0 != cudaSuccess) return cuda_fail(e0, "b200dp_mxent_fwd memset");
-    softdp_mxent_fwd_kernel<<<dim3((N + kLossRows - 1) / kLossRows, B), 256, 0, st>>>(p);
+    // 16-byte loads where every row of the three tensors starts on a 16-byte boundary
+    const bool vec = M % 4 == 0 && pb % 4 == 0 && pi % 4 == 0 && aligned(Ytrue, 16) && aligned(Ypred, 16) &&
+                     (!G || aligned(G, 16));
+    if (vec) softdp_mxent_fwd_kernel<true><<<dim3((N + kLossRows - 1) / kLossRows, B), 256, 0, st>>>(p);
+    else softdp_mxent_fwd_kernel<false><<<dim3((N + kLossRows - 1) / kLossRows, B), 256, 0, st>>>(p);
     softdp_mxent_fin_kernel<<<(B + 255) / 256 < 64 ? (B + 255) / 256 : 64, 256, 0, st>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "b200dp_mxent_fwd launch");
@@ -687,7 +691,11 @@ int b200dp_mxent_bwd(const float* Ytrue, const float* Ypred, long long pb, long 
     p.Ytrue = Ytrue; p.Ypred = Ypred; p.G = G; p.xlen = xlen; p.ylen = ylen;
     p.pb = pb; p.pi = pi; p.B = B; p.N = N; p.M = M;
     p.pair_count = const_cast<float*>(pair_count); p.gout = gout; p.grad = grad;
-    softdp_mxent_bwd_kernel<<<dim3((N + kLossRows - 1) / kLossRows, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    const bool vec = M % 4 == 0 && pb % 4 == 0 && pi % 4 == 0 && aligned(Ytrue, 16) && aligned(Ypred, 16) &&
+                     (!G || aligned(G, 16)) && aligned(grad, 16);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (vec) softdp_mxent_bwd_kernel<true><<<dim3((N + kLossRows - 1) / kLossRows, B), 256, 0, st>>>(p);
+    else softdp_mxent_bwd_kernel<false><<<dim3((N + kLossRows - 1) / kLossRows, B), 256, 0, st>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "b200dp_mxent_bwd launch");
     return 0;

@@ -44,37 +44,73 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return s;
 }
 
-// Grid (row slabs, pairs): a CTA takes kLossRows rows of one pair, warp w rows w, w + 8, ... of
-// the slab; lanes stride the columns, so every access is a coalesced 128-byte piece and no
-// index needs a division.  Slabs add their partial (sum, count) to the pair's totals with
-// atomics (pair_sum / pair_count zero-filled by the caller), a one-CTA kernel then forms
-// l_b / B.  (One CTA per pair, as in round 1, left a B = 32 batch on 32 of 148 SMs.)
+// Grid (row slabs, pairs): a CTA takes kLossRows rows of one pair, warp w the four rows
+// 4w .. 4w+3 of the slab.  All loads of a step -- G, Ytrue and Ypred of four rows, 16 bytes per
+// lane where the row pitches allow (M and the Ypred pitch multiples of 4, 16-byte aligned bases)
+// -- are issued before anything is used, unconditionally (the mask is applied to the values,
+// not to the loads), so a lane has 12 independent 16-byte loads in flight: the kernels are pure
+// streaming passes (12 B/cell forward, 16 B/cell backward) and need the memory-level
+// parallelism.  Slabs add their partial (sum, count) to the pair's totals with atomics
+// (zero-filled by b200dp_mxent_fwd), a small kernel then forms l_b / B.
 constexpr int kLossRows = 32;
 
+__device__ __forceinline__ float mxent_term(float y, float q0, float g, float& c) {
+    const bool on = g != 0.f;
+    const float q = fminf(fmaxf(q0, kLossEps), kLossMax);
+    c += on ? 1.f : 0.f;
+    return on ? y * logf(q) + (1.f - y) * logf(1.f - q) : 0.f;
+}
+__device__ __forceinline__ float mxent_grad(float y, float q0, float g, float scale) {
+    // clamp passes the gradient only inside [eps, max] (torch.clamp backward)
+    const bool on = g != 0.f && q0 >= kLossEps && q0 <= kLossMax;
+    return on ? scale * (y / q0 - (1.f - y) / (1.f - q0)) : 0.f;
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(256) softdp_mxent_fwd_kernel(LossParams p) {
     __shared__ float red[8];
     const int b = blockIdx.y;
     const int n = p.xlen ? min(max(p.xlen[b], 0), p.N) : p.N;
     const int m = p.ylen ? min(max(p.ylen[b], 0), p.M) : p.M;
-    const int i0 = blockIdx.x * kLossRows, i1 = min(i0 + kLossRows, n);
+    const int i0 = blockIdx.x * kLossRows;
     if (i0 >= n) return;
     const float* yt = p.Ytrue + (long long)b * p.N * p.M;
     const float* gm = p.G ? p.G + (long long)b * p.N * p.M : nullptr;
     const float* yp = p.Ypred + (long long)b * p.pb;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = i0 + 4 * w;
     float s = 0.f, c = 0.f;
-    for (int i = i0 + w; i < i1; i += nw) {
-        const float* ytr = yt + (long long)i * p.M;
-        const float* gmr = gm ? gm + (long long)i * p.M : nullptr;
-        const float* ypr = yp + (long long)i * p.pi;
-#pragma unroll 4
-        for (int j = lane; j < m; j += 32) {
-            if (!gmr || gmr[j] != 0.f) {
-                const float y = ytr[j];
-                const float q = fminf(fmaxf(ypr[j], kLossEps), kLossMax);
-                s += y * logf(q) + (1.f - y) * logf(1.f - q);
-                c += 1.f;
+    if (VEC) {
+        const int m4 = m >> 2;                           // whole float4 groups inside the pair's columns
+        for (int c4 = lane; c4 < m4; c4 += 32) {
+            float4 y4[4], q4[4], g4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = min(r0 + r, n - 1);       // rows past the pair: reload the last row, weight 0
+                y4[r] = reinterpret_cast<const float4*>(yt + (long long)i * p.M)[c4];
+                q4[r] = reinterpret_cast<const float4*>(yp + (long long)i * p.pi)[c4];
+                g4[r] = gm ? reinterpret_cast<const float4*>(gm + (long long)i * p.M)[c4] : make_float4(1.f, 1.f, 1.f, 1.f);
             }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float k = (r0 + r < n) ? 1.f : 0.f;
+                s += mxent_term(y4[r].x, q4[r].x, g4[r].x * k, c) + mxent_term(y4[r].y, q4[r].y, g4[r].y * k, c) +
+                     mxent_term(y4[r].z, q4[r].z, g4[r].z * k, c) + mxent_term(y4[r].w, q4[r].w, g4[r].w * k, c);
+            }
+        }
+        // the m % 4 tail columns
+        for (int j = 4 * m4 + lane; j < m; j += 32)
+            for (int r = 0; r < 4; ++r)
+                if (r0 + r < n) {
+                    const long long i = r0 + r;
+                    s += mxent_term(yt[i * p.M + j], yp[i * p.pi + j], gm ? gm[i * p.M + j] : 1.f, c);
+                }
+    } else {
+        for (int r = 0; r < 4; ++r) {
+            const long long i = r0 + r;
+            if (i >= n) break;
+            for (int j = lane; j < m; j += 32)
+                s += mxent_term(yt[i * p.M + j], yp[i * p.pi + j], gm ? gm[i * p.M + j] : 1.f, c);
         }
     }
     s = block_sum(s, red);
@@ -90,6 +126,7 @@ __global__ void softdp_mxent_fin_kernel(LossParams p) {
         p.pair_loss[b] = -(p.pair_loss[b] / p.pair_count[b]) / (float)p.B;   // mean of an empty selection is NaN, as in torch
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(256) softdp_mxent_bwd_kernel(LossParams p) {
     const int b = blockIdx.y;
     const int n = p.xlen ? min(max(p.xlen[b], 0), p.N) : p.N;
@@ -99,25 +136,41 @@ __global__ void __launch_bounds__(256) softdp_mxent_bwd_kernel(LossParams p) {
     const float* yp = p.Ypred + (long long)b * p.pb;
     float* gr = p.grad + (long long)b * p.N * p.M;
     const float scale = -p.gout[0] / (p.pair_count[b] * (float)p.B);
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    const int i0 = blockIdx.x * kLossRows, i1 = min(i0 + kLossRows, p.N);
-    for (int i = i0 + w; i < i1; i += nw) {
-        const float* ytr = yt + (long long)i * p.M;
-        const float* gmr = gm ? gm + (long long)i * p.M : nullptr;
-        const float* ypr = yp + (long long)i * p.pi;
-        float* grr = gr + (long long)i * p.M;
-#pragma unroll 4
-        for (int j = lane; j < p.M; j += 32) {
-            float g = 0.f;
-            if (i < n && j < m && (!gmr || gmr[j] != 0.f)) {
-                const float q0 = ypr[j];
-                // clamp passes the gradient only inside [eps, max] (torch.clamp backward)
-                if (q0 >= kLossEps && q0 <= kLossMax) {
-                    const float y = ytr[j];
-                    g = scale * (y / q0 - (1.f - y) / (1.f - q0));
-                }
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r0 = blockIdx.x * kLossRows + 4 * w;
+    if (VEC) {
+        const int M4 = p.M >> 2;
+        for (int c4 = lane; c4 < M4; c4 += 32) {
+            float4 y4[4], q4[4], g4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = min(r0 + r, p.N - 1);
+                y4[r] = reinterpret_cast<const float4*>(yt + (long long)i * p.M)[c4];
+                q4[r] = reinterpret_cast<const float4*>(yp + (long long)i * p.pi)[c4];
+                g4[r] = gm ? reinterpret_cast<const float4*>(gm + (long long)i * p.M)[c4] : make_float4(1.f, 1.f, 1.f, 1.f);
             }
-            grr[j] = g;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int i = r0 + r;
+                if (i >= p.N) break;
+                const int j = 4 * c4;
+                const float ki = i < n ? 1.f : 0.f;                      // zeros outside the pair's lattice
+                float4 o;
+                o.x = mxent_grad(y4[r].x, q4[r].x, g4[r].x * (j < m ? ki : 0.f), scale);
+                o.y = mxent_grad(y4[r].y, q4[r].y, g4[r].y * (j + 1 < m ? ki : 0.f), scale);
+                o.z = mxent_grad(y4[r].z, q4[r].z, g4[r].z * (j + 2 < m ? ki : 0.f), scale);
+                o.w = mxent_grad(y4[r].w, q4[r].w, g4[r].w * (j + 3 < m ? ki : 0.f), scale);
+                reinterpret_cast<float4*>(gr + (long long)i * p.M)[c4] = o;
+            }
+        }
+    } else {
+        for (int r = 0; r < 4; ++r) {
+            const long long i = r0 + r;
+            if (i >= p.N) break;
+            for (int j = lane; j < p.M; j += 32) {
+                const float g = (i < n && j < m) ? (gm ? gm[i * p.M + j] : 1.f) : 0.f;
+                gr[i * p.M + j] = mxent_grad(yt[i * p.M + j], yp[i * p.pi + j], g, scale);
+            }
         }
     }
 }
