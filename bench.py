@@ -563,6 +563,55 @@ def train_step_bench(cx, B, N, M, steps):
     return out
 
 
+def producer_bench(cx, B, L, D, steps):
+    """The step before the DP (alignment.py:122-123): theta / A from the embeddings, fused tcgen05
+    GEMM + activation (deepblast_b200.producer) next to torch's fp32 einsum + softplus / logsigmoid."""
+    import torch
+    import torch.nn.functional as F
+    from deepblast_b200 import producer
+    g = torch.Generator(device=cx.dev).manual_seed(7)
+    zs = [torch.randn(B, L, D, generator=g, device=cx.dev) * (1.1 / D ** 0.25) for _ in range(4)]
+
+    def timeit(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def ref():
+        return (F.softplus(torch.einsum('bid,bjd->bij', zs[0], zs[1])),
+                F.logsigmoid(torch.einsum('bid,bjd->bij', zs[2], zs[3])))
+    ours = timeit(lambda: producer.theta_a(*zs), steps)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        t_ref = timeit(ref, max(2, steps // 2))
+        th_r, a_r = ref()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    th, a = producer.theta_a(*zs)
+    flop = 2 * 2.0 * B * L * L * D                      # both products, useful
+    peak = 1656.8
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        with open(pk) as f:
+            peak = float(json.load(f).get("bf16_tflops", peak))
+    return {"B": B, "L": L, "D": D, "ms": ours, "torch_fp32_ms": t_ref,
+            "TFLOPs_useful": flop / ours / 1e9, "TFLOPs_issued_bf16": 3 * flop / ours / 1e9,
+            "roofline": {"bound": "tensor", "achieved": 3 * flop / ours / 1e9, "peak": peak, "unit": "TFLOP/s",
+                         "frac": 3 * flop / ours / 1e9 / peak,
+                         "note": "issued bf16 FLOPs (three passes of the hi/lo split) over the measured cuBLAS bf16 burst "
+                                 "peak; the time includes the fp32 -> bf16 hi/lo split pre-pass"},
+            "max_abs_err_theta_vs_torch_fp32": float((th - th_r).abs().max()),
+            "max_abs_err_A_vs_torch_fp32": float((a - a_r).abs().max())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -702,6 +751,12 @@ def main():
                     extras[tag] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
                 torch.cuda.synchronize()
                 torch.cuda.empty_cache()
+            try:
+                extras["producer_theta_A"] = producer_bench(cx, 1024, 256, 1024, 5)
+            except Exception as e:
+                extras["producer_theta_A"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
         if cx.rank == 0:
             line["workloads"] = extras
 
