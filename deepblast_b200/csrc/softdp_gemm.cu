@@ -22,6 +22,12 @@
 //     epilogue (TMEM lane quarter = warp % 4).  96 KB of shared memory per CTA: two CTAs per SM, so one
 //     CTA's epilogue overlaps the other's main loop.
 //
+// Two kernels: version 2 (default, below: the hi/lo split inside the GEMM, no workspace) and version 1
+// (a pre-pass writes bf16 copies, operands arrive through TMA; selected by passing a workspace).  Measured on
+// B200, B = 1024, L = 256, D = 1024: 1.58 ms against 2.73 ms (torch fp32 einsum + activations: 4.9 ms) --
+// the pre-pass alone moves 8.6 GB.  At this shape the producer is bound by reading the 4.3 GB of fp32
+// embeddings (each 128-row block is read by two tiles: 8.6 GB through L2), not by the tensor cores.
+//
 // Feeding the forward's operand ring directly (no theta / A round trip through HBM) was the survey's
 // second stage; it is deliberately not built: at D = 1024 the producer costs 2 x 3 x 2 x 1024 = 12288
 // tensor-core FLOP per cell against the DP's 16 bytes per cell, i.e. the GEMM side is compute-bound at
@@ -228,6 +234,186 @@ __global__ void __launch_bounds__(kGThreads) softdp_theta_a_kernel(const __grid_
     }
 }
 
+// ---- version 2: the split happens INSIDE the GEMM (no pre-pass, no bf16 copies in HBM) -------------
+// The pre-pass of version 1 reads every fp32 embedding once and writes hi and lo (8 B per element):
+// at L = 256 that is as much time as the tensor-core work itself.  Here eight converter warps load
+// the fp32 operand tiles straight from global memory (coalesced 16-byte loads, the next k block in
+// flight in registers while the current one is multiplied), form hi = bf16(x), lo = bf16(x - hi) and
+// store the four bf16 tiles (A hi, A lo, B hi, B lo) into shared memory in exactly the 128-byte-swizzle
+// K-major layout TMA would have produced (16-byte chunk c of row r lands at chunk c ^ (r & 7)); one
+// fence.proxy.async per thread makes the generic-proxy stores visible to the tensor core's async proxy,
+// then the warp arrives on the `full` barrier.  One shared-memory stage per CTA (64 KB) and two CTAs
+// per SM: while one CTA's twelve MMAs of a k block run (hi.hi, lo.hi, hi.lo x 4 k steps), the other
+// CTA converts, and tcgen05.commit on `empty` hands the stage back.
+constexpr int kG2Threads = 288;                            // warp 0: MMA issue + TMEM, warps 1..8: converters (1..4 also epilogue)
+constexpr int kG2Tile = kGM * kGK * 2;                     // one bf16 operand tile: 16 KB
+constexpr int kG2Smem = 4 * kG2Tile + 1024 + 256;
+
+struct Gemm2Params {
+    const float* x[2];         // [which]: zx / gx   [B, Lx, D]
+    const float* y[2];         // [which]: zy / gy   [B, Ly, D]
+    float* theta;
+    float* A;
+    const int* xlen;
+    const int* ylen;
+    const long long* pair_off;
+    int B, Lx, Ly, D;
+};
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+// 8 fp32 -> 8 bf16 hi (one 16-byte chunk) and 8 bf16 lo.  Only PACKED conversions (F2FP.BF16.PACK_AB,
+// full-rate ALU pipe): the single-element F2F conversions run on the quarter-rate XU pipe and made
+// the converter warps, not the tensor core, the bottleneck.  hi as a float is the packed word's half
+// shifted back into place (exact).
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(x0, x1);                                   // low half = bf16(x0), high half = bf16(x1)
+    const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+    lo = pack_bf16x2(x0 - h0, x1 - h1);
+}
+__device__ __forceinline__ void split8(const float4& u, const float4& v, uint4& hi, uint4& lo) {
+    split2(u.x, u.y, hi.x, lo.x);
+    split2(u.z, u.w, hi.y, lo.y);
+    split2(v.x, v.y, hi.z, lo.z);
+    split2(v.z, v.w, hi.w, lo.w);
+}
+
+__global__ void __launch_bounds__(kG2Threads, 2) softdp_theta_a2_kernel(Gemm2Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // tiles: [0] A hi, [1] A lo, [2] B hi, [3] B lo
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 4 * kG2Tile);
+    uint64_t* empty = full + 1;
+    uint64_t* tmem_full = full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.z >> 1, which = blockIdx.z & 1;
+    const int n = p.xlen ? min(max(p.xlen[b], 0), p.Lx) : p.Lx;
+    const int m = p.ylen ? min(max(p.ylen[b], 0), p.Ly) : p.Ly;
+    const int i0 = blockIdx.y * kGM, j0 = blockIdx.x * kGN;
+    if (i0 >= n || j0 >= m) return;
+
+    if (threadIdx.x == 0) {
+        mbar_init(full, 8);                              // one arrival per converter warp
+        mbar_init(empty, 1);                             // tcgen05.commit
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, kGN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+    const int KB = p.D / kGK;
+
+    if (warp == 0) {
+        // ===== MMA issuer =====
+        for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(full, kb & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t s0 = smem_u32(smem);
+                const uint64_t ah = umma_desc_sw128(s0), al = umma_desc_sw128(s0 + kG2Tile);
+                const uint64_t bh = umma_desc_sw128(s0 + 2 * kG2Tile), bl = umma_desc_sw128(s0 + 3 * kG2Tile);
+#pragma unroll
+                for (int k = 0; k < kGK / 16; ++k) {
+                    umma_bf16(tmem_acc, ah + 2 * k, bh + 2 * k, kIdesc, (kb | k) != 0);      // hi . hi
+                    umma_bf16(tmem_acc, al + 2 * k, bh + 2 * k, kIdesc, 1);                   // lo . hi
+                    umma_bf16(tmem_acc, ah + 2 * k, bl + 2 * k, kIdesc, 1);                   // hi . lo
+                }
+                umma_commit(empty);                      // the stage may be overwritten once these MMAs have read it
+                if (kb == KB - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== converters: global fp32 -> registers -> (hi, lo) bf16 -> swizzled shared memory =====
+        const int ct = threadIdx.x - 32;                 // 0..255
+        const float* xb = p.x[which] + (long long)b * p.Lx * p.D;
+        const float* yb = p.y[which] + (long long)b * p.Ly * p.D;
+        // unit u = ct + 256 i (i = 0..3) of each operand: row u / 8, 32-byte piece u % 8 of the 256-byte fp32 row
+        // (row = ct / 8 + 32 i, piece = ct % 8: the swizzled destination of unit i is unit 0's plus i * 4096)
+        const int row0 = ct >> 3, c8 = ct & 7;
+        const uint32_t dst0 = row0 * 128 + ((c8 ^ (row0 & 7)) << 4);
+        int soff[8];                                     // element offsets inside the pair's [L, D] operand
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = row0 + 32 * (i & 3);
+            const int grow = i >= 4 ? min(j0 + row, p.Ly - 1) : min(i0 + row, p.Lx - 1);   // overhanging rows: any valid row
+            soff[i] = grow * p.D + c8 * 8;
+        }
+        float4 r[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4* s4 = reinterpret_cast<const float4*>((i >= 4 ? yb : xb) + soff[i]);
+            r[2 * i] = __ldg(s4);
+            r[2 * i + 1] = __ldg(s4 + 1);
+        }
+        for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(empty, (kb & 1) ^ 1);              // the MMAs of k block kb-1 have read the stage
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint4 hi, lo;
+                split8(r[2 * i], r[2 * i + 1], hi, lo);
+                // rows 32 apart share (row & 7): the same swizzle, 4096 bytes further
+                unsigned char* d = smem + dst0 + (i & 3) * 4096 + (i >= 4 ? 2 * kG2Tile : 0);
+                *reinterpret_cast<uint4*>(d) = hi;
+                *reinterpret_cast<uint4*>(d + kG2Tile) = lo;
+            }
+            fence_proxy_async_smem();                    // generic-proxy stores -> visible to tcgen05 (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full);
+            if (kb + 1 < KB) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4* s4 = reinterpret_cast<const float4*>((i >= 4 ? yb : xb) + soff[i] + (kb + 1) * kGK);
+                    r[2 * i] = __ldg(s4);
+                    r[2 * i + 1] = __ldg(s4 + 1);
+                }
+            }
+        }
+        if (warp <= 4) {
+            // ===== epilogue (warps 1..4): TMEM -> registers -> activation -> smem transpose -> coalesced stores =====
+            const int q = warp & 3;
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+            float* tbuf = reinterpret_cast<float*>(smem) + (warp - 1) * (32 * 33);       // the stage is free now
+            float* out = which ? p.A : p.theta;
+            const int pitch = p.pair_off ? ((m + 3) & ~3) : p.Ly;
+            float* ob = out + (p.pair_off ? p.pair_off[b] : (long long)b * p.Lx * p.Ly);
+#pragma unroll 1
+            for (int c0 = 0; c0 < kGN; c0 += 32) {
+                if (j0 + c0 >= m) break;
+                float v[32];
+                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) tbuf[lane * 33 + c] = which ? logsigmoid_f(v[c]) : softplus_f(v[c]);
+                __syncwarp();
+                const int col = j0 + c0 + lane;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int row = i0 + q * 32 + rr;
+                    if (row < n && col < m) ob[(long long)row * pitch + col] = tbuf[rr * 33 + lane];
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_acc, kGN);
+    }
+}
+
 // fp32 -> (hi, lo) bf16 split of up to four tensors in one launch
 struct SplitParams {
     const float* src[4];
@@ -305,7 +491,22 @@ int b200dp_theta_a(const float* zx, const float* zy, const float* gx, const floa
     if (B == 0) return 0;
     if (D % kGK != 0) return fail(-5, "b200dp_theta_a: the embedding dimension must be a multiple of 64");
     if (2 * (long long)B > 65535) return fail(-5, "b200dp_theta_a: batch too large for one launch (2 B <= 65535)");
-    if (!zx || !zy || !gx || !gy || !theta || !A || !workspace) return fail(-1, "b200dp_theta_a: null pointer");
+    if (!zx || !zy || !gx || !gy || !theta || !A) return fail(-1, "b200dp_theta_a: null pointer");
+    if (!workspace) {
+        // version 2: the hi/lo split inside the GEMM, no workspace
+        if (!aligned(zx, 16) || !aligned(zy, 16) || !aligned(gx, 16) || !aligned(gy, 16))
+            return fail(-1, "b200dp_theta_a: embeddings must be 16-byte aligned");
+        Gemm2Params q;
+        q.x[0] = zx; q.x[1] = gx; q.y[0] = zy; q.y[1] = gy;
+        q.theta = theta; q.A = A; q.xlen = xlen; q.ylen = ylen; q.pair_off = pair_off;
+        q.B = B; q.Lx = Lx; q.Ly = Ly; q.D = D;
+        if (int rc = set_smem(softdp_theta_a2_kernel, kG2Smem, "b200dp_theta_a")) return rc;
+        const dim3 grid2((Ly + kGN - 1) / kGN, (Lx + kGM - 1) / kGM, 2 * B);
+        softdp_theta_a2_kernel<<<grid2, kG2Threads, kG2Smem, reinterpret_cast<cudaStream_t>(stream)>>>(q);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) return cuda_fail(e2, "b200dp_theta_a launch");
+        return 0;
+    }
     if (!aligned(zx, 16) || !aligned(zy, 16) || !aligned(gx, 16) || !aligned(gy, 16) || !aligned(workspace, 256))
         return fail(-1, "b200dp_theta_a: embeddings must be 16-byte, the workspace 256-byte aligned");
     if (workspace_bytes < b200dp_theta_a_workspace(B, Lx, Ly, D)) return fail(-1, "b200dp_theta_a: workspace too small");

@@ -14,6 +14,11 @@ from . import _lib
 from .ops import _ptr
 
 
+# False: the hi/lo split happens inside the GEMM kernel (default).  True: version 1, a pre-pass writes
+# bf16 copies of the embeddings into a workspace and the GEMM reads them through TMA.
+PREPASS = False
+
+
 def _check(name, t, shape=None):
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor (deepblast_b200 has no CPU path)")
@@ -56,8 +61,8 @@ def theta_a(zx, zy, gx, gy, xlen=None, ylen=None, plan=None):
             alloc = torch.zeros if xl is not None or yl is not None else torch.empty
             theta = alloc((B, Lx, Ly), dtype=torch.float32, device=dev)
             A = alloc((B, Lx, Ly), dtype=torch.float32, device=dev)
-        need = _lib.lib().b200dp_theta_a_workspace(B, Lx, Ly, D)
-        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        need = _lib.lib().b200dp_theta_a_workspace(B, Lx, Ly, D) if PREPASS else 0
+        ws = torch.empty(need, dtype=torch.uint8, device=dev) if PREPASS else None
         rc = _lib.lib().b200dp_theta_a(_ptr(zx), _ptr(zy), _ptr(gx), _ptr(gy), B, Lx, Ly, D, _ptr(xl), _ptr(yl),
                                        _ptr(poff), _ptr(theta), _ptr(A), _ptr(ws), need,
                                        torch.cuda.current_stream(dev).cuda_stream)

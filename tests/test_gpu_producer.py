@@ -50,6 +50,18 @@ def test_theta_a_vs_torch(B, Lx, Ly, D):
     np.testing.assert_allclose(A.cpu().numpy(), a_ref.cpu().numpy(), rtol=0, atol=1e-4)
 
 
+def test_theta_a_prepass_variant_vs_torch(monkeypatch):
+    """Version 1 of the kernel (bf16 hi/lo copies written by a pre-pass, operands through TMA into a
+    3-stage ring) stays selectable and correct."""
+    from deepblast_b200 import producer
+    monkeypatch.setattr(producer, "PREPASS", True)
+    zx, zy, gx, gy = embeddings(3, 200, 150, 128, seed=2)
+    theta, A = producer.theta_a(zx, zy, gx, gy)
+    th_ref, a_ref = reference(zx, zy, gx, gy)
+    np.testing.assert_allclose(theta.cpu().numpy(), th_ref.cpu().numpy(), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(A.cpu().numpy(), a_ref.cpu().numpy(), rtol=0, atol=1e-4)
+
+
 def test_theta_a_large_values_take_the_linear_branches():
     """softplus above torch's threshold (20) and logsigmoid far in both tails, on inner products of
     standard deviation 14: the error of the hi/lo split is bounded by the products' magnitudes,
