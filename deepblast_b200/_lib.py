@@ -37,6 +37,7 @@ EXPORTS = {
     "b200dp_sq_resident_warps": (ctypes.c_int, [_i]),
     "b200dp_sq_set_trace": (None, [_f]),
     "b200dp_sq_fwd": (ctypes.c_int, [_f, _i, _f, _f, _f, _f, _f, _i, _i, _f]),
+    "b200dp_sq_fwd_dense": (ctypes.c_int, [_f, _i, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
     "b200dp_sq_bwd": (ctypes.c_int, [_f, _i, _f, _f, _ll, _f, _f, _i, _i, _f]),
     "b200dp_sq_adj_fwd": (ctypes.c_int, [_f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _f]),
     "b200dp_sq_adj_bwd": (ctypes.c_int, [_f, _i, _f, _f, _f, _f, _i, _f]),

@@ -28,47 +28,12 @@ using namespace b200dp_host;
 
 namespace {
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    });
-    return fn;
-}
-
 // The chained kernels run one warp per pair: their time is one pair's latency, flat up to ~7
 // pairs per SM, while the hand-off kernels (W warps per pair) scale with the batch.  Measured
 // on B200 the two meet at about 4 pairs per SM (256 x 256: forward 0.177 ms chained against
 // 0.085 ms hand-off at 2 pairs per SM).
 constexpr int kChainedMinPairsPerSM = 4;
 
-
-// rank-3 map over a contiguous [B, N, M] fp32 tensor, box 32 cols x 32 rows x 1
-bool encode_row_map(CUtensorMap* map, const float* ptr, int B, int N, int M, int boxdim = kTile, int boxrows = 0) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)M, (cuuint64_t)N, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)M * 4, (cuuint64_t)N * M * 4};
-    cuuint32_t box[3] = {(cuuint32_t)boxdim, (cuuint32_t)(boxrows ? boxrows : boxdim), 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    // L2 promotion 256 B: a box row is only 64-128 B, but the neighbouring columns of the row
-    // are consumed a few blocks later, and DRAM serves 256-byte pieces far better than 64-byte
-    // ones (measured on B200, C2 forward: 0.272 ms with 128 B promotion, 0.246 ms with 256 B)
-    const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS;
-}
 
 QLayout q_layout(int N, int M) {
     QLayout ql;

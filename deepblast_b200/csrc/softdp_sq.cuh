@@ -166,8 +166,15 @@ __host__ __device__ inline size_t sq_fwd_smem_bytes() {
 
 // ---------------------------------------------------------------------------------------------
 // Forward fill (ADJ = false; STOREQ = false: score only, Vt alone) and adjoint forward (ADJ).
-template <bool SWM, bool ADJ, bool STOREQ, int RING>
-__global__ void __launch_bounds__(32) softdp_sq_fwd_kernel(const SqParams p) {
+// TMAOP: the operands are DENSE [B, N, M] tensors described by tensor maps -- one elected lane issues
+// 16 x 16 TMA boxes (same shared-memory image as the LDGSTS path) instead of every lane issuing four
+// 16-byte copies per tensor and block with their address arithmetic.  Measured on B200 at 1024 x 256^2:
+// 49 instead of 67 instructions per wavefront step and 64 instead of 128 registers; the time is the
+// same (0.228 ms) -- the sweep is bound by the latency of its dependent steps under the mixed
+// read / write traffic, not by issue slots.
+template <bool SWM, bool ADJ, bool STOREQ, int RING, bool TMAOP>
+__device__ __forceinline__ void sq_fwd_body(const SqParams& p, const CUtensorMap* tm_theta, const CUtensorMap* tm_A,
+                                            const CUtensorMap* tm_E) {
     static_assert(!(ADJ && SWM), "the adjoint sweeps cover the full range (sw.py:150-151)");
     constexpr int kGroupBytes = ADJ ? 3072 : 2048;
     constexpr int kSlot = 2 * kGroupBytes;
@@ -188,9 +195,14 @@ __global__ void __launch_bounds__(32) softdp_sq_fwd_kernel(const SqParams p) {
     float* zero_row = bv + 16;
 
     if (t == 0) {
-        for (int s = 0; s < RING; ++s) mbar_init(&bars[s], 32);
+        for (int s = 0; s < RING; ++s) mbar_init(&bars[s], TMAOP ? 1 : 32);
         if (ADJ)
             for (int s = 0; s < QR; ++s) mbar_init(&qbars[s], 1);
+        if (TMAOP) {
+            tma_prefetch_desc(tm_theta);
+            if (tm_A) tma_prefetch_desc(tm_A);
+            if (tm_E) tma_prefetch_desc(tm_E);
+        }
     }
     if (t < 16) {
         bv[t] = 0.f;
@@ -206,8 +218,30 @@ __global__ void __launch_bounds__(32) softdp_sq_fwd_kernel(const SqParams p) {
     // event e of a strip = {group 0 (rows 0..15): tile e, group 1 (rows 16..31): tile e-1} x tensors
     auto issue = [&](const StripRec& st, int e, unsigned slot) {
         if (p.dbg & 2) return;
-        unsigned char* dst = ring + slot * kSlot + r8 * 64 + ch * 16;
         const int T16 = (st.m + 15) >> 4;
+        if (TMAOP) {
+            const unsigned per = 1024u * (1u + (has_a ? 1u : 0u) + (has_e ? 1u : 0u));
+            unsigned bytes = 0;
+#pragma unroll
+            for (int gg = 0; gg < 2; ++gg)
+                if (e - gg >= 0 && e - gg < T16) bytes += per;
+            if (elect_one()) {
+                mbar_expect_tx(&bars[slot], bytes);
+#pragma unroll
+                for (int gg = 0; gg < 2; ++gg) {
+                    const int tile = e - gg;
+                    if (tile >= 0 && tile < T16) {
+                        unsigned char* d = ring + slot * kSlot + gg * kGroupBytes;
+                        const int row0 = st.k * kTile + gg * kG;
+                        tma_load_3d(d, tm_theta, &bars[slot], tile * kG, row0, st.pair);
+                        if (has_a) tma_load_3d(d + 1024, tm_A, &bars[slot], tile * kG, row0, st.pair);
+                        if (has_e) tma_load_3d(d + 2048, tm_E, &bars[slot], tile * kG, row0, st.pair);
+                    }
+                }
+            }
+            return;
+        }
+        unsigned char* dst = ring + slot * kSlot + r8 * 64 + ch * 16;
 #pragma unroll
         for (int gg = 0; gg < 2; ++gg) {
             const int tile = e - gg;
@@ -421,6 +455,17 @@ __global__ void __launch_bounds__(32) softdp_sq_fwd_kernel(const SqParams p) {
         nxt.rows = 0;
     }
     sq_exit(p.ctl, epoch);
+}
+
+template <bool SWM, bool ADJ, bool STOREQ, int RING>
+__global__ void __launch_bounds__(32) softdp_sq_fwd_kernel(const SqParams p) {
+    sq_fwd_body<SWM, ADJ, STOREQ, RING, false>(p, nullptr, nullptr, nullptr);
+}
+template <bool SWM, bool ADJ, bool STOREQ, int RING>
+__global__ void __launch_bounds__(32) softdp_sq_fwd_tma_kernel(const SqParams p, const __grid_constant__ CUtensorMap tm_theta,
+                                                               const __grid_constant__ CUtensorMap tm_A,
+                                                               const __grid_constant__ CUtensorMap tm_E) {
+    sq_fwd_body<SWM, ADJ, STOREQ, RING, true>(p, &tm_theta, p.A ? &tm_A : nullptr, p.E ? &tm_E : nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------

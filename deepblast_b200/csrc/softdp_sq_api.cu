@@ -43,8 +43,8 @@ int sq_occupancy(Kern k, size_t smem) {
     return occ;
 }
 
-template <class Kern>
-int sq_launch(Kern k, size_t smem, const SqParams& p, int flags, cudaStream_t st, const char* fn) {
+template <class Kern, class... Maps>
+int sq_launch(Kern k, size_t smem, const SqParams& p, int flags, cudaStream_t st, const char* fn, const Maps&... maps) {
     DevInfo di;
     if (!dev_info(di)) return fail(-2, std::string(fn) + ": cannot query the CUDA device");
     if (int rc = set_smem(k, smem, fn)) return rc;
@@ -55,7 +55,7 @@ int sq_launch(Kern k, size_t smem, const SqParams& p, int flags, cudaStream_t st
     if (forceG > 0) grid = forceG;
     if (grid > p.nstrips) grid = p.nstrips;
     if (grid < 1) grid = 1;
-    k<<<(int)grid, 32, smem, st>>>(p);
+    k<<<(int)grid, 32, smem, st>>>(p, maps...);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, fn);
     return 0;
@@ -291,6 +291,48 @@ int b200dp_sq_fwd(const void* tab, int nstrips, void* workspace, const float* th
     if (sw) B200DP_SQF(true, true, 4);
     B200DP_SQF(false, true, 4);
 #undef B200DP_SQF
+}
+
+int b200dp_sq_fwd_dense(const void* tab, int nstrips, void* workspace, const float* theta, const float* A,
+                        float* Q, float* Vt, int B, int N, int M, int mode, int flags, void* stream) {
+    if (int rc = sq_check("b200dp_sq_fwd_dense", tab, nstrips, workspace)) return rc;
+    if (mode != B200DP_MODE_NW && mode != B200DP_MODE_SW) return fail(-1, "b200dp_sq_fwd_dense: bad mode");
+    if (nstrips == 0) return 0;
+    if (!theta || !A || !Vt) return fail(-1, "b200dp_sq_fwd_dense: null pointer");
+    if (B < 1 || N < 1 || M < 4 || (M % 4) != 0) return fail(-1, "b200dp_sq_fwd_dense: need B, N >= 1 and M % 4 == 0");
+    if (!aligned(theta, 16) || !aligned(A, 16) || (Q && !aligned(Q, 16)))
+        return fail(-1, "b200dp_sq_fwd_dense: theta, A and Q must be 16-byte aligned");
+    CUtensorMap tmT, tmA;
+    if (!encode_row_map(&tmT, theta, B, N, M, kG) || !encode_row_map(&tmA, A, B, N, M, kG))
+        return b200dp_sq_fwd(tab, nstrips, workspace, theta, A, Q, Vt, mode, flags, stream);      // no TMA maps: LDGSTS staging
+    SqParams p = sq_params(tab, nstrips, workspace);
+    p.dbg = (flags >> B200DP_SQ_DBG_SHIFT) & 0xF;
+    p.trace = static_cast<unsigned long long*>(g_trace);
+    p.theta = theta;
+    p.A = A;
+    p.Q = Q;
+    p.Vt = Vt;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool sw = mode == B200DP_MODE_SW;
+    const int ring = ring_of(flags);
+#define B200DP_SQFT(SW_, STORE_, RING_)                                                                                  \
+    return sq_launch(softdp_sq_fwd_tma_kernel<SW_, false, STORE_, RING_>, sq_fwd_smem_bytes<false, RING_>(), p, flags, st, \
+                     "b200dp_sq_fwd_dense", tmT, tmA, tmT)
+    if (!Q) {
+        if (sw) B200DP_SQFT(true, false, 4);
+        B200DP_SQFT(false, false, 4);
+    }
+    if (ring == 3) {
+        if (sw) B200DP_SQFT(true, true, 3);
+        B200DP_SQFT(false, true, 3);
+    }
+    if (ring == 6) {
+        if (sw) B200DP_SQFT(true, true, 6);
+        B200DP_SQFT(false, true, 6);
+    }
+    if (sw) B200DP_SQFT(true, true, 4);
+    B200DP_SQFT(false, true, 4);
+#undef B200DP_SQFT
 }
 
 int b200dp_sq_bwd(const void* tab, int nstrips, void* workspace, const float* Et, long long et_stride,

@@ -293,6 +293,7 @@ def _sq_check_operand(name, t, plan):
 # plan: "auto" (ragged batches, and equal-size batches too small for the chained kernels),
 # "always" (every shape the kernels take), "never" (the round-1 kernels only).
 SQ_MODE = "auto"
+SQ_TMA_OPERANDS = True       # dense plans: stage theta / A with TMA boxes (False: the LDGSTS path, as for packed plans)
 _sm_count = {}
 
 
@@ -329,9 +330,16 @@ def sq_forward(plan, theta, A, mode="nw", need_q=True, flags=0):
         alloc = torch.zeros if plan.has_empty else torch.empty      # an empty pair scores 0 (nothing to sum)
         Vt = alloc(plan.B, dtype=torch.float32, device=theta.device)
         ws, stream = _sq_ws(plan, theta)
-        rc = _lib.lib().b200dp_sq_fwd(_ptr(plan.fwd_tab), plan.nstrips, _ptr(ws), _ptr(theta), _ptr(A),
-                                      _ptr(Q), _ptr(Vt), MODES[mode], _sq_flags(plan, flags, True), stream)
-        _lib.check(rc, "b200dp_sq_fwd")
+        if not plan.packed and SQ_TMA_OPERANDS:
+            # dense [B, N, M] operands: TMA boxes instead of per-lane 16-byte copies
+            rc = _lib.lib().b200dp_sq_fwd_dense(_ptr(plan.fwd_tab), plan.nstrips, _ptr(ws), _ptr(theta), _ptr(A),
+                                                _ptr(Q), _ptr(Vt), plan.B, plan.N, plan.M, MODES[mode],
+                                                _sq_flags(plan, flags, True), stream)
+            _lib.check(rc, "b200dp_sq_fwd_dense")
+        else:
+            rc = _lib.lib().b200dp_sq_fwd(_ptr(plan.fwd_tab), plan.nstrips, _ptr(ws), _ptr(theta), _ptr(A),
+                                          _ptr(Q), _ptr(Vt), MODES[mode], _sq_flags(plan, flags, True), stream)
+            _lib.check(rc, "b200dp_sq_fwd")
     return Vt, Q
 
 

@@ -218,6 +218,11 @@ void b200dp_sq_set_trace(void* trace);
 int b200dp_sq_fwd(const void* fwd_tab, int nstrips, void* workspace,
                   const float* theta, const float* A, float* Q, float* Vt, int mode, int flags,
                   void* stream);
+/* The same sweep for a plan in the DENSE layout (theta, A contiguous [B, N, M], M % 4 == 0): the operand
+ * tiles travel as 16 x 16 TMA boxes issued by one elected lane instead of per-lane 16-byte copies. */
+int b200dp_sq_fwd_dense(const void* fwd_tab, int nstrips, void* workspace,
+                        const float* theta, const float* A, float* Q, float* Vt,
+                        int B, int N, int M, int mode, int flags, void* stream);
 /* _backward_pass_kernel (nw_cuda.py:82-102): Et, Q -> E (interior layout). */
 int b200dp_sq_bwd(const void* bwd_tab, int nstrips, void* workspace,
                   const float* Et, long long et_stride, const float* Q, float* E, int mode,

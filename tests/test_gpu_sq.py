@@ -259,3 +259,33 @@ def test_sq_autograd_decode_and_double_backward(planmod, mode, cls, packed):
         np.testing.assert_allclose(plan.pair_view(aln.detach(), b).cpu().numpy(), E_o, rtol=0, atol=2 * ATOL)
         sc = max(1.0, float(np.abs(Ed_o).max()))
         np.testing.assert_allclose(plan.pair_view(th.grad, b).cpu().numpy(), Ed_o, rtol=0, atol=1e-4 * sc)
+
+
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+def test_sq_dense_tma_staging_equals_ldgsts_staging(ops, planmod, mode):
+    """Dense plans stage theta / A with TMA boxes (b200dp_sq_fwd_dense), packed plans and the fallback
+    with per-lane 16-byte copies (b200dp_sq_fwd): the same shared-memory image, so Q and Vt must agree
+    bit for bit -- equal-size lattices, ragged lengths inside a dense tensor, M not a multiple of 16."""
+    d = dev()
+    for B, N, M, ragged in ((3, 96, 200, False), (4, 130, 260, True), (2, 256, 256, False), (5, 64, 68, True)):
+        theta, A, _, _ = rand_batch(B, N, M, seed=7)
+        rng = np.random.default_rng(3)
+        xl = rng.integers(1, N + 1, B) if ragged else None
+        yl = rng.integers(1, M + 1, B) if ragged else None
+        plan = planmod.Plan(B, N, M, xl, yl, packed=False, device=d)
+        out = {}
+        for tma in (True, False):
+            ops.SQ_TMA_OPERANDS = tma
+            try:
+                Vt, Q = ops.sq_forward(plan, theta.to(d), A.to(d), mode)
+                Vs, _ = ops.sq_forward(plan, theta.to(d), A.to(d), mode, need_q=False)
+            finally:
+                ops.SQ_TMA_OPERANDS = True
+            torch.cuda.synchronize()
+            out[tma] = (Vt.cpu(), Q.cpu(), Vs.cpu())
+        assert torch.equal(out[True][0], out[False][0])
+        assert torch.equal(out[True][2], out[False][2])
+        for b in range(B):                                  # (storage between pairs' streams is never written)
+            qa = ops.sq_q_to_reference(plan, out[True][1].to(d), b).cpu()
+            qb = ops.sq_q_to_reference(plan, out[False][1].to(d), b).cpu()
+            assert torch.equal(qa, qb)
