@@ -503,6 +503,36 @@ def e2e_packed(cx, w, nst):
         "pinned host Vt and packed dVt/dtheta, per rank")
 
 
+def e2e_infer(cx, w, nst):
+    """Inference from host buffers: what DeepBLAST.align needs per pair is the alignment PATH
+    (trainer.py:80-88), so the walk runs on the device and only the paths and scores come back
+    (deepblast_b200.align.HostAligner)."""
+    import torch
+    import torch.distributed as dist
+    from deepblast_b200.align import HostAligner
+    B, N, M = w.B, w.N, w.M
+    h_theta = torch.empty((B, N, M), dtype=torch.float32, pin_memory=True).copy_(w.theta.detach().cpu())
+    h_A = torch.empty((B, N, M), dtype=torch.float32, pin_memory=True).copy_(w.A.cpu())
+    al = HostAligner(B, N, M, w.mode, device=cx.dev)
+    for _ in range(2):
+        al.align(h_theta, h_A)
+    torch.cuda.synchronize()
+    if cx.world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(nst):
+        al.align(h_theta, h_A)
+    e1.record()
+    torch.cuda.synchronize()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=cx.dev)
+    if cx.world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    h2d = int(2 * B * N * M * 4)
+    d2h = int(al.paths_h.numel() * 4 + B * 8)
+    return float(te.item()) / nst, h2d, d2h
+
+
 def train_step_bench(cx, B, N, M, steps):
     """Training-shaped step (trainer.py:154-188): decode (forward + backward, create_graph) ->
     MatrixCrossEntropy -> loss.backward() (the adjoint pair).  Eager, and replayed from one CUDA graph."""
@@ -678,6 +708,22 @@ def main():
                 "host_ceiling_ms_per_step": ceil_ms, "frac_of_host_ceiling": ceil_ms / ms, "note": note}
 
     e2e = None if args.no_e2e else e2e_of(w, max(3, min(steps, 10)))
+    e2e_inf = None
+    if not args.no_e2e and w.plan is None and w.M % 4 == 0:
+        try:
+            nst = max(3, min(steps, 10))
+            ms, h2d, d2h = e2e_infer(cx, w, nst)
+            cells = torch.tensor([float(w.cells)], dtype=torch.float64, device=cx.dev)
+            if cx.world > 1:
+                dist.all_reduce(cells, op=dist.ReduceOp.SUM)
+            ceil_ms = host_ceiling(cx, h2d, d2h)
+            e2e_inf = {"value": float(cells.item()) / (ms * 1e-3), "unit": "cell-updates/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "ms_per_step": ms, "steps": nst,
+                       "host_ceiling_ms_per_step": ceil_ms, "frac_of_host_ceiling": ceil_ms / ms,
+                       "note": "pinned host theta/A -> align.HostAligner (chunked H2D | fwd+bwd+traceback on the device | "
+                               "D2H of the alignment paths and scores only), per rank"}
+        except Exception as e:
+            e2e_inf = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
     line = None
     if cx.rank == 0:
@@ -707,6 +753,8 @@ def main():
             line["graph_error"] = r["graph_error"]
         if e2e:
             line["e2e"] = e2e
+        if e2e_inf:
+            line["e2e_inference"] = e2e_inf
     del r
 
     # ---- every other BASELINE config under the same clock ---------------------------------------------

@@ -25,6 +25,9 @@ EXPORTS = {
     "b200dp_adj_bwd": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f]),
     "b200dp_decode_host_workspace": (ctypes.c_size_t, [_i, _i, _i]),
     "b200dp_decode_host": (ctypes.c_int, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _f, ctypes.c_size_t, _i, _f]),
+    "b200dp_align_host_workspace": (ctypes.c_size_t, [_i, _i, _i]),
+    "b200dp_align_host_path_cap": (ctypes.c_int, [_i, _i]),
+    "b200dp_align_host": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _f, ctypes.c_size_t, _i, _f]),
     "b200dp_adj3_applicable": (ctypes.c_int, [_i, _i, _i]),
     "b200dp_adj_fwd3": (ctypes.c_int, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _i, _f]),
     "b200dp_adj_bwd3": (ctypes.c_int, [_f, _f, _f, _f, _i, _i, _i, _i, _f]),

@@ -680,8 +680,9 @@ namespace {
 
 struct HostPipe {
     bool ready = false;
-    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr, s_walk = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t walk_done[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t in_done[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t cmp_done[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t out_done[3] = {nullptr, nullptr, nullptr};
@@ -694,9 +695,10 @@ __global__ void fill_one_kernel(float* p) { p[0] = 1.0f; }
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct HostSlotLayout {
-    size_t theta, A, Q, E, Vt, Et, bytes;
+    size_t theta, A, Q, E, Vt, Et, paths, len, bytes;
 };
-HostSlotLayout host_slot_layout(int N, int M, int cp) {
+inline int host_path_cap(int N, int M) { return 2 * (N + M) + 8; }
+HostSlotLayout host_slot_layout(int N, int M, int cp, bool with_paths = false) {
     const QLayout ql = q_layout(N, M);
     HostSlotLayout L;
     size_t off = 0;
@@ -706,6 +708,10 @@ HostSlotLayout host_slot_layout(int N, int M, int cp) {
     L.E = off;     off = align256(off + (size_t)cp * (N + 2) * (M + 2) * 4);
     L.Vt = off;    off = align256(off + (size_t)cp * 4);
     L.Et = off;    off = align256(off + (size_t)cp * 4);
+    L.paths = off;
+    if (with_paths) off = align256(off + (size_t)cp * host_path_cap(N, M) * 3 * 4);
+    L.len = off;
+    if (with_paths) off = align256(off + (size_t)cp * 4);
     L.bytes = off;
     return L;
 }
@@ -719,17 +725,29 @@ size_t b200dp_decode_host_workspace(int N, int M, int chunk_pairs) {
     return 3 * host_slot_layout(N, M, chunk_pairs).bytes + 256;
 }
 
-int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h, float* Vt_h, float* E_h, int B,
-                       int N, int M, int mode, int chunk_pairs, void* workspace, size_t workspace_bytes, int flags,
-                       void* stream) {
+size_t b200dp_align_host_workspace(int N, int M, int chunk_pairs) {
+    if (N < 1 || M < 1 || chunk_pairs < 1) return 0;
+    return 3 * host_slot_layout(N, M, chunk_pairs, true).bytes + 256;
+}
+
+int b200dp_align_host_path_cap(int N, int M) { return host_path_cap(N, M); }
+
+// Shared pipeline of b200dp_decode_host (E_h: the padded expected-alignment matrices come back) and
+// b200dp_align_host (paths_h / len_h: the walk runs on the device, only the paths come back).
+static int host_pipeline(const float* theta_h, const float* A_h, const float* Et_h, float* Vt_h, float* E_h,
+                         int32_t* paths_h, int32_t* len_h, int variant, int B, int N, int M, int mode, int chunk_pairs,
+                         void* workspace, size_t workspace_bytes, int flags, void* stream) {
+    const bool walk = paths_h != nullptr;
     if (int rc = check_common("b200dp_decode_host", B, N, M)) return rc;
     if (mode != B200DP_MODE_NW && mode != B200DP_MODE_SW) return fail(-1, "b200dp_decode_host: bad mode");
     if (B == 0) return 0;
-    if (!theta_h || !A_h || !Vt_h || !E_h || !workspace) return fail(-1, "b200dp_decode_host: null pointer");
+    if (!theta_h || !A_h || !Vt_h || (!E_h && !walk) || (walk && !len_h) || !workspace)
+        return fail(-1, "b200dp_decode_host: null pointer");
+    if (walk && variant != 0 && variant != 1) return fail(-1, "b200dp_align_host: bad variant");
     if (chunk_pairs < 1) return fail(-1, "b200dp_decode_host: chunk_pairs < 1");
     if (!aligned(workspace, 256)) return fail(-1, "b200dp_decode_host: workspace must be 256-byte aligned");
-    if (workspace_bytes < b200dp_decode_host_workspace(N, M, chunk_pairs))
-        return fail(-1, "b200dp_decode_host: workspace too small (see b200dp_decode_host_workspace)");
+    if (workspace_bytes < (walk ? b200dp_align_host_workspace(N, M, chunk_pairs) : b200dp_decode_host_workspace(N, M, chunk_pairs)))
+        return fail(-1, "b200dp_decode_host: workspace too small (see b200dp_decode_host_workspace / b200dp_align_host_workspace)");
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(-2, "b200dp_decode_host: no device");
     std::lock_guard<std::mutex> lk(g_pipe_mu);      // one pipeline per device, enqueued by one thread at a time
@@ -740,18 +758,21 @@ int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp.s_cmp, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&hp.s_walk, cudaStreamNonBlocking);
         mk(&hp.fork);
         mk(&hp.join);
         for (int i = 0; i < 3; ++i) {
             mk(&hp.in_done[i]);
             mk(&hp.cmp_done[i]);
             mk(&hp.out_done[i]);
+            mk(&hp.walk_done[i]);
         }
         if (e != cudaSuccess) return cuda_fail(e, "b200dp_decode_host: stream/event creation");
         hp.ready = true;
     }
     cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
-    const HostSlotLayout L = host_slot_layout(N, M, chunk_pairs);
+    const HostSlotLayout L = host_slot_layout(N, M, chunk_pairs, walk);
+    const int cap = host_path_cap(N, M);
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     float* one = reinterpret_cast<float*>(ws + 3 * L.bytes);
     const size_t pairTA = (size_t)N * M, pairE = (size_t)(N + 2) * (M + 2);
@@ -770,6 +791,7 @@ int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h
     B200DP_CK(cudaStreamWaitEvent(hp.s_in, hp.fork, 0), "b200dp_decode_host: fork");
     B200DP_CK(cudaStreamWaitEvent(hp.s_cmp, hp.fork, 0), "b200dp_decode_host: fork");
     B200DP_CK(cudaStreamWaitEvent(hp.s_out, hp.fork, 0), "b200dp_decode_host: fork");
+    B200DP_CK(cudaStreamWaitEvent(hp.s_walk, hp.fork, 0), "b200dp_decode_host: fork");
     if (!Et_h) {
         fill_one_kernel<<<1, 1, 0, hp.s_cmp>>>(one);
         B200DP_CK(cudaGetLastError(), "b200dp_decode_host: fill launch");
@@ -802,11 +824,30 @@ int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h
         if (int rc = b200dp_bwd(Et_h ? d_Et : one, Et_h ? 1 : 0, d_Q, d_E, nullptr, nullptr, nb, N, M, mode, flags,
                                 hp.s_cmp))
             return rc;
+        int32_t* d_paths = reinterpret_cast<int32_t*>(sb + L.paths);
+        int32_t* d_len = reinterpret_cast<int32_t*>(sb + L.len);
         B200DP_CK(cudaEventRecord(hp.cmp_done[sl], hp.s_cmp), "b200dp_decode_host: record");
+        if (walk) {
+            // the greedy walk of nw_cuda.py:273-317 over the interior of the padded E, all pairs of the chunk.
+            // A walk is a chain of dependent loads (about a microsecond per step whatever the chunk size): it
+            // runs on a stream of its own, beside the sweeps of the following chunks
+            B200DP_CK(cudaStreamWaitEvent(hp.s_walk, hp.cmp_done[sl], 0), "b200dp_align_host: wait");
+            if (int rc = b200dp_traceback(d_E + (M + 2) + 1, (long long)pairE, (long long)(M + 2), 1, nullptr, nullptr, nb, N, M,
+                                          variant, d_paths, cap, d_len, hp.s_walk))
+                return rc;
+            B200DP_CK(cudaEventRecord(hp.walk_done[sl], hp.s_walk), "b200dp_align_host: record");
+        }
         // download
-        B200DP_CK(cudaStreamWaitEvent(hp.s_out, hp.cmp_done[sl], 0), "b200dp_decode_host: wait");
-        B200DP_CK(cudaMemcpyAsync(E_h + (size_t)b0 * pairE, d_E, (size_t)nb * pairE * 4, cudaMemcpyDeviceToHost,
-                                  hp.s_out), "b200dp_decode_host: D2H E");
+        B200DP_CK(cudaStreamWaitEvent(hp.s_out, walk ? hp.walk_done[sl] : hp.cmp_done[sl], 0), "b200dp_decode_host: wait");
+        if (walk) {
+            B200DP_CK(cudaMemcpyAsync(paths_h + (size_t)b0 * cap * 3, d_paths, (size_t)nb * cap * 3 * 4, cudaMemcpyDeviceToHost,
+                                      hp.s_out), "b200dp_align_host: D2H paths");
+            B200DP_CK(cudaMemcpyAsync(len_h + b0, d_len, (size_t)nb * 4, cudaMemcpyDeviceToHost, hp.s_out),
+                      "b200dp_align_host: D2H lengths");
+        }
+        if (E_h)
+            B200DP_CK(cudaMemcpyAsync(E_h + (size_t)b0 * pairE, d_E, (size_t)nb * pairE * 4, cudaMemcpyDeviceToHost,
+                                      hp.s_out), "b200dp_decode_host: D2H E");
         B200DP_CK(cudaMemcpyAsync(Vt_h + b0, d_Vt, (size_t)nb * 4, cudaMemcpyDeviceToHost, hp.s_out),
                   "b200dp_decode_host: D2H Vt");
         B200DP_CK(cudaEventRecord(hp.out_done[sl], hp.s_out), "b200dp_decode_host: record");
@@ -817,8 +858,8 @@ int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h
     // join: the caller's stream continues after the last download (s_out runs in order, and every
     // download waited for its sweeps, which waited for their uploads); after an error all three
     // internal streams are joined, whatever they got to
-    cudaStream_t tojoin[3] = {hp.s_out, hp.s_cmp, hp.s_in};
-    for (int i = 0; i < (rc ? 3 : 1); ++i) {
+    cudaStream_t tojoin[4] = {hp.s_out, hp.s_cmp, hp.s_in, hp.s_walk};
+    for (int i = 0; i < (rc ? 4 : 1); ++i) {
         cudaError_t e1 = cudaEventRecord(hp.join, tojoin[i]);
         if (e1 == cudaSuccess) e1 = cudaStreamWaitEvent(user, hp.join, 0);
         if (e1 != cudaSuccess && !rc) return cuda_fail(e1, "b200dp_decode_host: join");
@@ -826,6 +867,22 @@ int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h
     if (rc) return rc;
 #undef B200DP_CK
     return 0;
+}
+
+int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h, float* Vt_h, float* E_h, int B,
+                       int N, int M, int mode, int chunk_pairs, void* workspace, size_t workspace_bytes, int flags,
+                       void* stream) {
+    return host_pipeline(theta_h, A_h, Et_h, Vt_h, E_h, nullptr, nullptr, 0, B, N, M, mode, chunk_pairs, workspace,
+                         workspace_bytes, flags, stream);
+}
+
+int b200dp_align_host(const float* theta_h, const float* A_h, float* Vt_h, int32_t* paths_h, int32_t* len_h, float* E_h,
+                      int B, int N, int M, int mode, int variant, int chunk_pairs, void* workspace,
+                      size_t workspace_bytes, int flags, void* stream) {
+    if (mode != B200DP_MODE_NW && mode != B200DP_MODE_SW) return fail(-1, "b200dp_align_host: bad mode");
+    if (!paths_h || !len_h) return fail(-1, "b200dp_align_host: null pointer");
+    return host_pipeline(theta_h, A_h, nullptr, Vt_h, E_h, paths_h, len_h, variant, B, N, M, mode, chunk_pairs, workspace,
+                         workspace_bytes, flags, stream);
 }
 
 }  // extern "C"

@@ -157,6 +157,20 @@ int b200dp_decode_host(const float* theta_h, const float* A_h, const float* Et_h
                        float* E_h, int B, int N, int M, int mode, int chunk_pairs,
                        void* workspace, size_t workspace_bytes, int flags, void* stream);
 
+/* Inference from HOST buffers: what DeepBLAST.align needs per pair is the alignment PATH
+ * (deepblast/trainer.py:80-88 -> alignment.py:160-171 -> the walk of nw_cuda.py:273-317).  The same
+ * chunked pipeline as b200dp_decode_host, with the walk run on the device (b200dp_traceback on each
+ * chunk's E) so that only the paths and scores cross PCIe:
+ *   -> Vt_h [B], paths_h [B, cap, 3] int32 triples (i, j, state), cap = b200dp_align_host_path_cap(N, M),
+ *      len_h [B] (steps of each path; -2 / -1 as b200dp_traceback), and, when E_h is not NULL, the
+ *      padded E as well.  variant: B200DP_TRACEBACK_*_RULE. */
+size_t b200dp_align_host_workspace(int N, int M, int chunk_pairs);
+int b200dp_align_host_path_cap(int N, int M);
+int b200dp_align_host(const float* theta_h, const float* A_h, float* Vt_h, int32_t* paths_h,
+                      int32_t* len_h, float* E_h, int B, int N, int M, int mode, int variant,
+                      int chunk_pairs, void* workspace, size_t workspace_bytes, int flags,
+                      void* stream);
+
 /* ---- strip-queue family: batches of any shape -- ragged (per-pair lengths), PACKED, small
  * batches of long pairs, large batches of equal pairs (softdp_sq.cuh).  Same passes as above
  * (one export per reference kernel, deepblast/nw_cuda.py:46-165); with per-pair lengths each

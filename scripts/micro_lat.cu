@@ -33,8 +33,9 @@ __global__ void chain(float* out, long long* cyc, float seed) {
 }
 
 // forward cell step (softdp_fwd2.cuh fwd2_step, steady form), NC independent chains per warp
-template <int NC, bool STORE>
+template <int NC, int STORE>
 __global__ void fwd_step(float* out, long long* cyc, const float* __restrict__ th, const float* __restrict__ aa, float* q) {
+    q += (size_t)blockIdx.x * 1024 * 64;
     float h[NC], v[NC];
     for (int c = 0; c < NC; ++c) { h[c] = 0.1f * c; v[c] = 0.2f; }
     const float t_ = th[threadIdx.x], a_ = aa[threadIdx.x];
@@ -58,9 +59,11 @@ __global__ void fwd_step(float* out, long long* cyc, const float* __restrict__ t
             h[c] = l - v[c];
             v[c] = l - hup;
             part += h[c];
-            if (STORE) {
+            if (STORE == 1) {
                 q[(size_t)(i & 1023) * 64 + threadIdx.x] = qx;
                 q[(size_t)(i & 1023) * 64 + 32 + threadIdx.x] = qy;
+            } else if (STORE == 2) {
+                reinterpret_cast<float2*>(q)[(size_t)(i & 1023) * 32 + threadIdx.x] = make_float2(qx, qy);
             } else {
                 part += qx * 1e-9f + qy * 1e-9f;
             }
@@ -167,9 +170,10 @@ int main() {
     CH(5, "FMNMX+FADD chain");
     CH(6, "SHFL.UP+FADD chain");
     CH(7, "SHFL.IDX+FADD chain");
-    run("fwd step log-domain, 1 chain", [&](int w) { fwd_step<1, false><<<SM * w, 32>>>(out, cyc, th, aa, q); }, cyc);
-    run("fwd step log-domain, 2 chains", [&](int w) { fwd_step<2, false><<<SM * w, 32>>>(out, cyc, th, aa, q); }, cyc);
-    run("fwd step log-domain +STG, 1 chain", [&](int w) { fwd_step<1, true><<<SM * w, 32>>>(out, cyc, th, aa, q + (size_t)0); }, cyc);
+    run("fwd step log-domain, 1 chain", [&](int w) { fwd_step<1, 0><<<SM * w, 32>>>(out, cyc, th, aa, q); }, cyc);
+    run("fwd step log-domain, 2 chains", [&](int w) { fwd_step<2, 0><<<SM * w, 32>>>(out, cyc, th, aa, q); }, cyc);
+    run("fwd step log-domain +STG, 1 chain", [&](int w) { fwd_step<1, 1><<<SM * w, 32>>>(out, cyc, th, aa, q + (size_t)0); }, cyc);
+    run("fwd step log-domain +STG.64, 1 chain", [&](int w) { fwd_step<1, 2><<<SM * w, 32>>>(out, cyc, th, aa, q + (size_t)0); }, cyc);
     run("fwd step linear ratio, 1 chain", [&](int w) { lin_step<1><<<SM * w, 32>>>(out, cyc, th, aa); }, cyc);
     run("fwd step linear ratio, 2 chains", [&](int w) { lin_step<2><<<SM * w, 32>>>(out, cyc, th, aa); }, cyc);
     run("bwd step, 1 chain", [&](int w) { bwd_step<1><<<SM * w, 32>>>(out, cyc, th, aa); }, cyc);

