@@ -44,6 +44,10 @@ EXPORTS = {
     "b200dp_sq_bwd": (ctypes.c_int, [_f, _i, _f, _f, _ll, _f, _f, _i, _i, _f]),
     "b200dp_sq_adj_fwd": (ctypes.c_int, [_f, _i, _f, _f, _f, _f, _f, _f, _f, _i, _f]),
     "b200dp_sq_adj_bwd": (ctypes.c_int, [_f, _i, _f, _f, _f, _f, _i, _f]),
+    # cluster kernels (small batches of long pairs)
+    "b200dp_cl_applicable": (ctypes.c_int, [_i, _i, _i]),
+    "b200dp_cl_fwd": (ctypes.c_int, [_f, _f, _f, _f, _i, _i, _i, _i, _i, _f]),
+    "b200dp_cl_bwd": (ctypes.c_int, [_f, _ll, _f, _f, _i, _i, _i, _i, _i, _f]),
     # theta / A producer (tcgen05 GEMM)
     "b200dp_theta_a_workspace": (ctypes.c_size_t, [_i, _i, _i, _i]),
     "b200dp_theta_a": (ctypes.c_int, [_f, _f, _f, _f, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f, ctypes.c_size_t, _f]),

@@ -372,8 +372,13 @@ __device__ __forceinline__ void sq_fwd_body(const SqParams& p, const CUtensorMap
             const unsigned char* sB = ring + slotB * kSlot + lanebase;
             const bool steady = full_rows && b >= 2 && s0 + 16 <= m;
             float part = 0.f;
-            if (steady) {
-                // every lane inside the lattice for 16 steps: operands hoisted, no predicates
+            // One unrolled body for both kinds of block, operands hoisted into registers: EDGE = false when every
+            // lane is inside the lattice for the 16 steps (no predicates), EDGE = true for the ramp blocks at
+            // both ends of a strip and for partial strips (the same step with the lattice-membership selects;
+            // the 31 + 8 steps by which a strip trails its predecessor are ramp steps, so their speed sets
+            // the dependency stagger of a long pair).
+            auto block = [&](auto edge_tag) {
+                constexpr bool EDGE = decltype(edge_tag)::value;
                 float th_[16], a_[16], bv_[16];
                 float e_[ADJ ? 16 : 1], qx_[ADJ ? 16 : 1], qy_[ADJ ? 16 : 1];
 #pragma unroll
@@ -396,48 +401,41 @@ __device__ __forceinline__ void sq_fwd_body(const SqParams& p, const CUtensorMap
                     bv_[4 * q4 + 3] = b4.w;
                 }
                 const bool live = !(SWM && first && t == 0);      // sw.py: row 1 is below the origin
-                unsigned long long* bw = bout + (s0 - 31);
+                const bool cap = EDGE && last && (((m - 1 + (rows - 1)) >> 4) == b);
+                const int c0 = s0 - t;                            // the lane's column at step 0 of the block
 #pragma unroll
                 for (int ss = 0; ss < 16; ++ss) {
                     float hup = __shfl_up_sync(kFull, h, 1);
                     hup = (t == 0) ? bv_[ss] : hup;
-                    if (ADJ)
-                        h = adj3_step<false>(th_[ss], a_[ss], e_[ss], qx_[ss], qy_[ss], hup, v, qp + ss * kStepFloats,
-                                             true, true);
-                    else
-                        h = fwd2_step<false, SWM, FDBG>(th_[ss], a_[ss], hup, v, qp + ss * kStepFloats, true, live);
-                    part += h;
-                    if (t == 31 && feeds_down) sq_publish(bw + ss, sq_pack(epoch, h), p.dbg);
+                    if (!EDGE) {
+                        if (ADJ)
+                            h = adj3_step<false>(th_[ss], a_[ss], e_[ss], qx_[ss], qy_[ss], hup, v, qp + ss * kStepFloats,
+                                                 true, true);
+                        else
+                            h = fwd2_step<false, SWM, FDBG>(th_[ss], a_[ss], hup, v, qp + ss * kStepFloats, true, live);
+                        part += h;
+                        if (t == 31 && feeds_down) sq_publish(bout + (c0 + ss), sq_pack(epoch, h), p.dbg);
+                    } else {
+                        const int c = c0 + ss;
+                        const bool in = row_ok && (unsigned)c < (unsigned)m;
+                        const bool comp = SWM ? (in && rowcomp && c >= 1) : in;      // sw.py: j >= 2
+                        if (ADJ)
+                            h = adj3_step<true>(th_[ss], a_[ss], e_[ss], in ? qx_[ss] : 0.f, in ? qy_[ss] : 0.f, hup, v,
+                                                qp + ss * kStepFloats, in, comp);
+                        else
+                            h = fwd2_step<true, SWM, FDBG>(th_[ss], a_[ss], hup, v, qp + ss * kStepFloats, in, comp);
+                        part += h;
+                        if (t == 31 && feeds_down && in) sq_publish(bout + c, sq_pack(epoch, h), p.dbg);
+                        // Vt = V[n, m] = ln 2 * sum_j h[n, j]   (adjoint: Vtd = sum_j hd[n, j])
+                        if (cap && in && t == rows - 1 && c == m - 1)
+                            p.Vt[cur.pair] = (acc_hi + (acc_lo + part)) * (ADJ ? 1.f : kLn2);
+                    }
                     if (ss == kSqPfStep && pf_next) pfv = ld_relaxed_gpu_u64(bin + nx);
                 }
                 qp += 16 * kStepFloats;
-            } else {
-                // ramp blocks: the same step with the lattice-membership selects
-                const bool cap = last && (((m - 1 + (rows - 1)) >> 4) == b);
-#pragma unroll 4
-                for (int ss = 0; ss < 16; ++ss) {
-                    const int c = s0 + ss - t;
-                    float hup = __shfl_up_sync(kFull, h, 1);
-                    if (t == 0) hup = br[ss];
-                    const bool in = row_ok && (unsigned)c < (unsigned)m;
-                    const bool comp = SWM ? (in && rowcomp && c >= 1) : in;      // sw.py: j >= 2
-                    const float* tb = reinterpret_cast<const float*>((tp <= ss) ? sB : sA);
-                    if (ADJ) {
-                        h = adj3_step<true>(tb[ss], has_a ? tb[ss + 256] : 0.f, has_e ? tb[ss + 512] : 1.f,
-                                            in ? qt[ss * kStepFloats] : 0.f, in ? qt[ss * kStepFloats + kQY] : 0.f, hup, v,
-                                            qp, in, comp);
-                    } else {
-                        h = fwd2_step<true, SWM, FDBG>(tb[ss], tb[ss + 256], hup, v, qp, in, comp);
-                    }
-                    part += h;
-                    if (t == 31 && feeds_down && in) sq_publish(bout + c, sq_pack(epoch, h), p.dbg);
-                    // Vt = V[n, m] = ln 2 * sum_j h[n, j]   (adjoint: Vtd = sum_j hd[n, j])
-                    if (cap && in && t == rows - 1 && c == m - 1)
-                        p.Vt[cur.pair] = (acc_hi + (acc_lo + part)) * (ADJ ? 1.f : kLn2);
-                    if (ss == kSqPfStep && pf_next) pfv = ld_relaxed_gpu_u64(bin + nx);
-                    qp += kStepFloats;
-                }
-            }
+            };
+            if (steady) block(std::false_type{});
+            else block(std::true_type{});
             {
                 // fold the block's partial row sum into the two-float accumulator (Fast2Sum)
                 const float t1 = part + acc_lo;
@@ -674,7 +672,9 @@ __global__ void __launch_bounds__(32) softdp_sq_bwd_kernel(const SqParams p) {
                 // ramp blocks.  Q in the ramps was never written by the forward (arbitrary
                 // bits): products are selected, not multiplied by zero.
                 const bool seed_blk = !ADJ && bottom && s0 < 32;      // E[n, m] = Et lives here
-#pragma unroll 4
+                // (fully unrolled: 2-3 % faster than by 4; hoisting the Q loads as in the steady block makes ptxas
+                // re-schedule the steady block too, 0.169 -> 0.183 ms at 1024 x 256^2)
+#pragma unroll
                 for (int ss = 0; ss < 16; ++ss) {
                     const int c = m - 1 - (s0 + ss - u);
                     float zin = __shfl_down_sync(kFull, zout, 1);

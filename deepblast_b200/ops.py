@@ -10,6 +10,7 @@ are stored; the m state is implied (Q sums to 1 over the states, Qd to 0), and q
 marks a cell whose Q is identically zero (first row / column of the sw.py lattice).
 """
 import ctypes
+import functools
 import threading
 
 import torch
@@ -294,6 +295,21 @@ def _sq_check_operand(name, t, plan):
 # "always" (every shape the kernels take), "never" (the round-1 kernels only).
 SQ_MODE = "auto"
 SQ_TMA_OPERANDS = True       # dense plans: stage theta / A with TMA boxes (False: the LDGSTS path, as for packed plans)
+CLUSTER = True               # small dense batches of equal-size pairs: the cluster FORWARD kernel (DSMEM hand-off)
+CLUSTER_BWD = False          # the cluster backward is 5-20 % slower than the strip-queue backward on B200: not dispatched
+
+
+@functools.lru_cache(maxsize=256)
+def _cl_size(dev_index, B, N, M):
+    with torch.cuda.device(dev_index):
+        return int(_lib.lib().b200dp_cl_applicable(B, N, M))
+
+
+def _use_cluster(plan, flags):
+    """Cluster size for this plan, or 0: dense, equal-size, bound by one pair's dependency chain."""
+    if not CLUSTER or plan.packed or plan.ragged or flags or plan.device.type != "cuda":
+        return 0
+    return _cl_size(plan.device.index, plan.B, plan.N, plan.M)
 _sm_count = {}
 
 
@@ -329,6 +345,11 @@ def sq_forward(plan, theta, A, mode="nw", need_q=True, flags=0):
         Q = torch.empty(plan.q_floats, dtype=torch.float32, device=theta.device) if need_q else None
         alloc = torch.zeros if plan.has_empty else torch.empty      # an empty pair scores 0 (nothing to sum)
         Vt = alloc(plan.B, dtype=torch.float32, device=theta.device)
+        if _use_cluster(plan, flags):
+            rc = _lib.lib().b200dp_cl_fwd(_ptr(theta), _ptr(A), _ptr(Q), _ptr(Vt), plan.B, plan.N, plan.M, MODES[mode],
+                                          0, _stream(theta))
+            _lib.check(rc, "b200dp_cl_fwd")
+            return Vt, Q
         ws, stream = _sq_ws(plan, theta)
         if not plan.packed and SQ_TMA_OPERANDS:
             # dense [B, N, M] operands: TMA boxes instead of per-lane 16-byte copies
@@ -360,6 +381,11 @@ def sq_backward(plan, Et, Q, mode="nw", flags=0):
     Et = Et.detach()
     with torch.cuda.device(Q.device):
         E = _sq_out_like(plan, Q)
+        if CLUSTER_BWD and _use_cluster(plan, flags):
+            rc = _lib.lib().b200dp_cl_bwd(_ptr(Et), Et.stride(0) if plan.B > 0 else 0, _ptr(Q), _ptr(E), plan.B, plan.N,
+                                          plan.M, MODES[mode], 0, _stream(Q))
+            _lib.check(rc, "b200dp_cl_bwd")
+            return E
         ws, stream = _sq_ws(plan, Q)
         rc = _lib.lib().b200dp_sq_bwd(_ptr(plan.bwd_tab), plan.nstrips, _ptr(ws), _ptr(Et),
                                       Et.stride(0) if plan.B > 0 else 0, _ptr(Q), _ptr(E), MODES[mode],

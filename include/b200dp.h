@@ -250,6 +250,20 @@ int b200dp_sq_adj_fwd(const void* fwd_tab, int nstrips, void* workspace,
 int b200dp_sq_adj_bwd(const void* bwd_tab, int nstrips, void* workspace,
                       const float* Q, const float* QdE, float* Ed, int flags, void* stream);
 
+/* ---- cluster kernels: SMALL batches of LONG equal-size lattices (what the reference trains and infers
+ * on: a few dozen pairs of up to 1024 x 1024, deepblast/trainer.py:375; one pair at a time,
+ * alignment.py:165-169).  One thread-block cluster per pair, its strips dealt round-robin to the
+ * cluster's CTAs, boundary rows handed over through distributed shared memory (softdp_cl.cuh).
+ * theta / A dense [B, N, M] (M % 4 == 0, N > 32); Q as everywhere (NULL: score only); E is the INTERIOR
+ * [B, N, M] like the strip-queue kernels'.  b200dp_cl_applicable: 0 when the strip-queue kernels should
+ * take the batch (it is not bound by one pair's dependency chain), else the cluster size.
+ * flags: bits 4..7 force the cluster size (1, 2, 4, 8). */
+int b200dp_cl_applicable(int B, int N, int M);
+int b200dp_cl_fwd(const float* theta, const float* A, float* Q, float* Vt, int B, int N, int M,
+                  int mode, int flags, void* stream);
+int b200dp_cl_bwd(const float* Et, long long et_stride, const float* Q, float* E, int B, int N, int M,
+                  int mode, int flags, void* stream);
+
 /* ---- the step before the DP: theta = softplus(zx zy^T), A = logsigmoid(gx gy^T)
  * (deepblast/alignment.py:122-123,134-135,162-163) as one batched tcgen05 GEMM launch with the
  * activation fused into the epilogue (softdp_gemm.cu).  zx, gx [B, Lx, D], zy, gy [B, Ly, D] fp32

@@ -289,3 +289,62 @@ def test_sq_dense_tma_staging_equals_ldgsts_staging(ops, planmod, mode):
             qa = ops.sq_q_to_reference(plan, out[True][1].to(d), b).cpu()
             qb = ops.sq_q_to_reference(plan, out[False][1].to(d), b).cpu()
             assert torch.equal(qa, qb)
+
+
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+@pytest.mark.parametrize("B,N,M,cs,W", [(3, 96, 128, 0, 0), (2, 130, 260, 0, 0), (100, 64, 128, 8, 1), (37, 70, 72, 8, 2),
+                                        (5, 300, 200, 4, 4), (2, 1024, 512, 0, 0), (9, 33, 64, 2, 2)])
+def test_cluster_kernels_equal_strip_queue_kernels(ops, planmod, mode, B, N, M, cs, W):
+    """Cluster kernels (softdp_cl.cuh: the strips of a pair dealt round-robin to the warps of a thread-block
+    cluster, boundary rows handed over through distributed shared memory) against the strip-queue kernels:
+    the same cell arithmetic in the same order, so Vt, Q and E must agree bit for bit -- partial strips,
+    pairs with fewer strips than the ring has warps (flow control: a producer must not lap its consumer),
+    more pairs than resident clusters, forced cluster sizes and warps per CTA, score-only."""
+    from deepblast_b200 import _lib
+    L = _lib.lib()
+    d = dev()
+    theta, A, _, _ = rand_batch(B, N, M, seed=9)
+    th_d, a_d = theta.to(d), A.to(d)
+    Et = torch.linspace(0.5, 1.5, B, device=d)
+    plan = planmod.Plan(B, N, M, device=d)
+    old = ops.CLUSTER
+    ops.CLUSTER = False
+    try:
+        Vt0, Q0 = ops.sq_forward(plan, th_d, a_d, mode)
+        E0 = ops.sq_backward(plan, Et, Q0, mode)
+    finally:
+        ops.CLUSTER = old
+    fl = (cs << 4) | (W << 8)
+    st = torch.cuda.current_stream().cuda_stream
+    Q = torch.zeros_like(Q0)
+    Vt, Vs = torch.empty_like(Vt0), torch.empty_like(Vt0)
+    E = torch.full_like(E0, float("nan"))
+    for _ in range(2):                                      # twice: the second launch finds warm caches and other timing
+        _lib.check(L.b200dp_cl_fwd(th_d.data_ptr(), a_d.data_ptr(), Q.data_ptr(), Vt.data_ptr(), B, N, M, ops.MODES[mode], fl, st),
+                   "b200dp_cl_fwd")
+        _lib.check(L.b200dp_cl_fwd(th_d.data_ptr(), a_d.data_ptr(), None, Vs.data_ptr(), B, N, M, ops.MODES[mode], fl, st),
+                   "b200dp_cl_fwd")
+        _lib.check(L.b200dp_cl_bwd(Et.data_ptr(), Et.stride(0), Q.data_ptr(), E.data_ptr(), B, N, M, ops.MODES[mode], fl, st),
+                   "b200dp_cl_bwd")
+    torch.cuda.synchronize()
+    assert torch.equal(Vt, Vt0) and torch.equal(Vs, Vt0)
+    assert torch.equal(E, E0)
+    for b in range(0, B, max(1, B // 7)):
+        assert torch.equal(ops.sq_q_to_reference(plan, Q, b), ops.sq_q_to_reference(plan, Q0, b))
+
+
+def test_small_batches_are_routed_to_the_cluster_forward(ops, planmod):
+    """ops.sq_forward sends small dense equal-size batches to b200dp_cl_fwd (b200dp_cl_applicable) and the
+    result still matches the per-pair oracle; ragged and packed plans never take that path."""
+    from deepblast_b200 import _lib
+    d = dev()
+    assert _lib.lib().b200dp_cl_applicable(2, 256, 256) > 0
+    assert _lib.lib().b200dp_cl_applicable(1024, 256, 256) == 0
+    assert _lib.lib().b200dp_cl_applicable(4, 32, 256) == 0          # a single strip has nothing to hand over
+    B, N, M = 2, 96, 200
+    theta, A, Zt, ZA = rand_batch(B, N, M, seed=4)
+    plan = planmod.Plan(B, N, M, device=d)
+    assert ops._use_cluster(plan, 0) > 0
+    run_and_check(ops, plan, theta, A, Zt, ZA, "nw")
+    rag = planmod.Plan(B, N, M, [90, 40], [200, 64], device=d)
+    assert ops._use_cluster(rag, 0) == 0
