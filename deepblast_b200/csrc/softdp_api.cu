@@ -505,8 +505,7 @@ int b200dp_traceback(const float* grad, long long sb, long long si, long long sj
     p.out = out;
     p.cap = cap;
     p.len = len;
-    const int threads = 32;
-    softdp_traceback_kernel<<<(B + threads - 1) / threads, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    softdp_traceback_kernel<<<(B + kTbWarps - 1) / kTbWarps, 32 * kTbWarps, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "b200dp_traceback launch");
     return 0;
