@@ -619,7 +619,12 @@ __global__ void __launch_bounds__(32) softdp_sq_bwd_kernel(const SqParams p) {
             float* st = stage + srow * kB2StagePitch + t;
             // lane 31's column at step s is m-1-s; lane 0's is m+30-s
             const bool steady = full_rows && s0 >= 32 && s0 + 15 <= m - 1 - (SWM ? 1 : 0);
-            if (steady) {
+            // One unrolled body for both kinds of block (see the forward kernel): EDGE = true for the ramp blocks.
+            // Q in the ramps was never written by the forward (arbitrary bits): products are selected there,
+            // not multiplied by zero.  (The empty asm statements pin the hoisted loads in front of the steps:
+            // without them ptxas sinks the shared-memory loads into the dependent chain.)
+            auto block = [&](auto edge_tag) {
+                constexpr bool EDGE = decltype(edge_tag)::value;
                 float bv_[16];
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
@@ -642,70 +647,63 @@ __global__ void __launch_bounds__(32) softdp_sq_bwd_kernel(const SqParams p) {
                 }
 #pragma unroll
                 for (int ss = 0; ss < 16; ++ss) {
+                    asm volatile("" : "+f"(qx_[ss]), "+f"(qy_[ss]));
+                    if (ADJ) asm volatile("" : "+f"(px_[ss]), "+f"(py_[ss]));
+                }
+#pragma unroll
+                for (int ss = 0; ss < 16; ++ss) {
                     qm_[ss] = (1.f - qx_[ss]) - qy_[ss];      // >= 0 by the forward's clamp
-                    if (ADJ) {
+                    if (ADJ) pm_[ss] = -(px_[ss] + py_[ss]);  // Qd sums to 0 over the states
+                    if (ADJ && !EDGE) {
                         const bool live = qx_[ss] >= 0.f;     // a marked cell (Q == 0) pushes nothing
                         qx_[ss] = live ? qx_[ss] : 0.f;
                         qy_[ss] = live ? qy_[ss] : 0.f;
                         qm_[ss] = live ? qm_[ss] : 0.f;
-                        pm_[ss] = -(px_[ss] + py_[ss]);       // Qd sums to 0 over the states
                     }
                 }
+                const bool seed_blk = EDGE && !ADJ && bottom && s0 < 32;      // E[n, m] = Et lives here
+                const int c0 = m - 1 - s0 + u;                // the lane's column at step 0 of the block
                 unsigned long long* bw = bout + (m + 30 - s0);
 #pragma unroll
                 for (int ss = 0; ss < 16; ++ss) {
                     float zin = __shfl_down_sync(kFull, zout, 1);
                     if (t == 31) zin = bv_[ss];
                     float e = zin + yprev;
-                    if (SWM) e = sw_dead ? 0.f : e;           // row 1: E = 0, nothing pushed (0 * mark = 0)
-                    const float X = ADJ ? fmaf(qx_[ss], e, px_[ss]) : qx_[ss] * e;
-                    const float Y = ADJ ? fmaf(qy_[ss], e, py_[ss]) : qy_[ss] * e;
-                    const float D = ADJ ? fmaf(qm_[ss], e, pm_[ss]) : qm_[ss] * e;
-                    st[ss * kB2StagePitch] = e;
-                    zout = X + dprev;
-                    dprev = D;
-                    yprev = Y;
-                    if (t == 0 && feeds_up) sq_publish(bw - ss, sq_pack(epoch, zout), p.dbg);
-                    if (ss == kSqPfStep && pf_next) pfv = ld_relaxed_gpu_u64(bin + cn);
-                }
-            } else {
-                // ramp blocks.  Q in the ramps was never written by the forward (arbitrary
-                // bits): products are selected, not multiplied by zero.
-                const bool seed_blk = !ADJ && bottom && s0 < 32;      // E[n, m] = Et lives here
-                // (fully unrolled: 2-3 % faster than by 4; hoisting the Q loads as in the steady block makes ptxas
-                // re-schedule the steady block too, 0.169 -> 0.183 ms at 1024 x 256^2)
-#pragma unroll
-                for (int ss = 0; ss < 16; ++ss) {
-                    const int c = m - 1 - (s0 + ss - u);
-                    float zin = __shfl_down_sync(kFull, zout, 1);
-                    if (t == 31) zin = br[ss];
-                    const bool in = row_ok && (unsigned)c < (unsigned)m;
-                    const bool comp = SWM ? (in && rowcomp && c >= 1) : in;
-                    float e = zin + yprev;
-                    if (seed_blk && t == rows - 1 && c == m - 1) e = et;   // nw.py:125-127
-                    e = comp ? e : 0.f;
-                    const float qx = qt[(15 - ss) * kStepFloats], qy = qt[(15 - ss) * kStepFloats + kQY];
                     float X, Y, D;
-                    if (ADJ) {
-                        const bool live = comp && qx >= 0.f;
-                        const float px = qt[kDiagElems + (15 - ss) * kStepFloats];
-                        const float py = qt[kDiagElems + (15 - ss) * kStepFloats + kQY];
-                        X = live ? fmaf(qx, e, px) : 0.f;
-                        Y = live ? fmaf(qy, e, py) : 0.f;
-                        D = live ? fmaf((1.f - qx) - qy, e, -(px + py)) : 0.f;
+                    if (!EDGE) {
+                        if (SWM) e = sw_dead ? 0.f : e;       // row 1: E = 0, nothing pushed (0 * mark = 0)
+                        X = ADJ ? fmaf(qx_[ss], e, px_[ss]) : qx_[ss] * e;
+                        Y = ADJ ? fmaf(qy_[ss], e, py_[ss]) : qy_[ss] * e;
+                        D = ADJ ? fmaf(qm_[ss], e, pm_[ss]) : qm_[ss] * e;
                     } else {
-                        X = comp ? qx * e : 0.f;
-                        Y = comp ? qy * e : 0.f;
-                        D = comp ? ((1.f - qx) - qy) * e : 0.f;
+                        const int c = c0 - ss;
+                        const bool in = row_ok && (unsigned)c < (unsigned)m;
+                        const bool comp = SWM ? (in && rowcomp && c >= 1) : in;
+                        if (seed_blk && t == rows - 1 && c == m - 1) e = et;   // nw.py:125-127
+                        e = comp ? e : 0.f;
+                        if (ADJ) {
+                            const bool live = comp && qx_[ss] >= 0.f;
+                            X = live ? fmaf(qx_[ss], e, px_[ss]) : 0.f;
+                            Y = live ? fmaf(qy_[ss], e, py_[ss]) : 0.f;
+                            D = live ? fmaf(qm_[ss], e, pm_[ss]) : 0.f;
+                        } else {
+                            X = comp ? qx_[ss] * e : 0.f;
+                            Y = comp ? qy_[ss] * e : 0.f;
+                            D = comp ? qm_[ss] * e : 0.f;
+                        }
                     }
                     st[ss * kB2StagePitch] = e;
                     zout = X + dprev;
                     dprev = D;
                     yprev = Y;
-                    if (t == 0 && feeds_up && in) sq_publish(bout + c, sq_pack(epoch, zout), p.dbg);
+                    // (lane 0's column at this step is m + 30 - s0 - ss: a warp-uniform address, immediate offset)
+                    if (t == 0 && feeds_up && (!EDGE || (row_ok && (unsigned)(m + 30 - s0 - ss) < (unsigned)m)))
+                        sq_publish(bw - ss, sq_pack(epoch, zout), p.dbg);
                     if (ss == kSqPfStep && pf_next) pfv = ld_relaxed_gpu_u64(bin + cn);
                 }
-            }
+            };
+            if (steady) block(std::false_type{});
+            else block(std::true_type{});
             srow += 16;
             if (srow == kB2StageSteps) srow = 0;
         }
