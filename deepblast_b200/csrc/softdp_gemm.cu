@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kGThreads) softdp_theta_a_kernel(const __grid_
 // then the warp arrives on the `full` barrier.  One shared-memory stage per CTA (64 KB) and two CTAs
 // per SM: while one CTA's twelve MMAs of a k block run (hi.hi, lo.hi, hi.lo x 4 k steps), the other
 // CTA converts, and tcgen05.commit on `empty` hands the stage back.
-constexpr int kG2Threads = 288;                            // warp 0: MMA issue + TMEM, warps 1..8: converters (1..4 also epilogue)
+constexpr int kG2Threads = 288;                            // warp 0: MMA issue + TMEM, warps 1..8: converters, then epilogue
 constexpr int kG2Tile = kGM * kGK * 2;                     // one bf16 operand tile: 16 KB
 constexpr int kG2Smem = 4 * kG2Tile + 1024 + 256;
 
@@ -379,9 +379,11 @@ __global__ void __launch_bounds__(kG2Threads, 2) softdp_theta_a2_kernel(Gemm2Par
                 }
             }
         }
-        if (warp <= 4) {
-            // ===== epilogue (warps 1..4): TMEM -> registers -> activation -> smem transpose -> coalesced stores =====
-            const int q = warp & 3;
+        {
+            // ===== epilogue (all eight converter warps): TMEM -> registers -> activation -> smem transpose ->
+            // coalesced stores.  A warp may read the TMEM lane quarter warp % 4: warps 1..4 take columns 0..63 of
+            // their quarter, warps 5..8 columns 64..127 =====
+            const int q = warp & 3, half = (warp - 1) >> 2;
             mbar_wait(tmem_full, 0);
             tc_fence_after();
             float* tbuf = reinterpret_cast<float*>(smem) + (warp - 1) * (32 * 33);       // the stage is free now
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(kG2Threads, 2) softdp_theta_a2_kernel(Gemm2Par
             const int pitch = p.pair_off ? ((m + 3) & ~3) : p.Ly;
             float* ob = out + (p.pair_off ? p.pair_off[b] : (long long)b * p.Lx * p.Ly);
 #pragma unroll 1
-            for (int c0 = 0; c0 < kGN; c0 += 32) {
+            for (int c0 = half * (kGN / 2); c0 < (half + 1) * (kGN / 2); c0 += 32) {
                 if (j0 + c0 >= m) break;
                 float v[32];
                 tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
