@@ -107,8 +107,10 @@ class HostAligner:
         with torch.cuda.device(self.device):
             self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=self.device) for _ in range(3))
             mk = lambda *s, dt=torch.float32: torch.empty(s, dtype=dt, device=self.device)      # noqa: E731
-            self.slots = [(mk(cb, N, M), mk(cb, N, M), mk(cb, self.cap, 3, dt=torch.int32), mk(cb, dt=torch.int32))
-                          for _ in range(3)]
+            qcap = max(int(pl.q_floats) for _, _, pl in self.chunks)
+            # (results live in per-slot buffers too: nothing is allocated inside align())
+            self.slots = [(mk(cb, N, M), mk(cb, N, M), mk(cb, self.cap, 3, dt=torch.int32), mk(cb, dt=torch.int32),
+                           mk(qcap), mk(cb, N, M), mk(cb)) for _ in range(3)]
             self.cmp_done = [torch.cuda.Event() for _ in range(3)]
             self.out_done = [torch.cuda.Event() for _ in range(3)]
             self.ones = torch.ones(B, dtype=torch.float32, device=self.device)
@@ -136,7 +138,7 @@ class HostAligner:
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_stream(cur)
         for c, (b0, b1, pl) in enumerate(self.chunks):
-            th_d, a_d, out_d, ln_d = self.slots[c % 3]
+            th_d, a_d, out_d, ln_d, q_d, e_d, vt_d = self.slots[c % 3]
             n = b1 - b0
             with torch.cuda.stream(self.s_in):
                 self.s_in.wait_event(self.cmp_done[c % 3])            # the slot's previous sweeps are done
@@ -147,8 +149,8 @@ class HostAligner:
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(up)
                 self.s_cmp.wait_event(self.out_done[c % 3])           # the slot's previous paths have left
-                Vt, Q = ops.sq_forward(pl, th_d[:n], a_d[:n], self.mode)
-                E = ops.sq_backward(pl, self.ones[b0:b1], Q, self.mode)          # [n, N, M] interior
+                Vt, Q = ops.sq_forward(pl, th_d[:n], a_d[:n], self.mode, out=(vt_d, q_d))
+                E = ops.sq_backward(pl, self.ones[b0:b1], Q, self.mode, out=e_d[:n])          # [n, N, M] interior
                 rc = L.b200dp_traceback(E.data_ptr(), E.stride(0), E.stride(1), E.stride(2),
                                         None if self.xl_d is None else self.xl_d[b0:b1].data_ptr(),
                                         None if self.yl_d is None else self.yl_d[b0:b1].data_ptr(),
@@ -160,8 +162,7 @@ class HostAligner:
                 self.s_out.wait_event(self.cmp_done[c % 3])
                 self.paths_h[b0:b1].copy_(out_d[:n], non_blocking=True)
                 self.len_h[b0:b1].copy_(ln_d[:n], non_blocking=True)
-                self.Vt_h[b0:b1].copy_(Vt, non_blocking=True)
-                Vt.record_stream(self.s_out)
+                self.Vt_h[b0:b1].copy_(Vt[:n], non_blocking=True)
                 self.out_done[c % 3].record(self.s_out)
         cur.wait_stream(self.s_out)
         return self.paths_h, self.len_h, self.Vt_h

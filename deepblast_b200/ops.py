@@ -334,17 +334,30 @@ def route_plan(theta, xlen=None, ylen=None):
     return _plan.get_plan(B, N, M, xlen, ylen, False, theta.device)
 
 
-def sq_forward(plan, theta, A, mode="nw", need_q=True, flags=0):
+def _sq_take_out(name, t, numel, device):
+    if t.device != device or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < numel:
+        raise RuntimeError(f"out {name}: need a contiguous float32 tensor of at least {numel} elements on {device}")
+    return t
+
+
+def sq_forward(plan, theta, A, mode="nw", need_q=True, flags=0, out=None):
     """theta, A in the plan's layout (dense [B,N,M] or a flat packed buffer) -> (Vt [B], Q flat
-    strip-major buffer, or None with need_q=False: score only).  nw.py:65-117 per pair."""
+    strip-major buffer, or None with need_q=False: score only).  nw.py:65-117 per pair.
+    out = (Vt, Q): caller-owned result buffers (pipelines that must not allocate inside their loop)."""
     theta = theta.detach().contiguous()
     A = A.detach().contiguous()
     _sq_check_operand("theta", theta, plan)
     _sq_check_operand("A", A, plan)
     with torch.cuda.device(theta.device):
-        Q = torch.empty(plan.q_floats, dtype=torch.float32, device=theta.device) if need_q else None
-        alloc = torch.zeros if plan.has_empty else torch.empty      # an empty pair scores 0 (nothing to sum)
-        Vt = alloc(plan.B, dtype=torch.float32, device=theta.device)
+        if out is not None:
+            Vt = _sq_take_out("Vt", out[0], plan.B, theta.device)
+            Q = _sq_take_out("Q", out[1], plan.q_floats, theta.device) if need_q else None
+            if plan.has_empty:
+                Vt[:plan.B].zero_()
+        else:
+            Q = torch.empty(plan.q_floats, dtype=torch.float32, device=theta.device) if need_q else None
+            alloc = torch.zeros if plan.has_empty else torch.empty      # an empty pair scores 0 (nothing to sum)
+            Vt = alloc(plan.B, dtype=torch.float32, device=theta.device)
         if _use_cluster(plan, flags):
             rc = _lib.lib().b200dp_cl_fwd(_ptr(theta), _ptr(A), _ptr(Q), _ptr(Vt), plan.B, plan.N, plan.M, MODES[mode],
                                           0, _stream(theta))
@@ -374,13 +387,18 @@ def _sq_out_like(plan, ref):
     return alloc((plan.B, plan.N, plan.M), dtype=torch.float32, device=ref.device)
 
 
-def sq_backward(plan, Et, Q, mode="nw", flags=0):
+def sq_backward(plan, Et, Q, mode="nw", flags=0, out=None):
     """Et [B] (any stride), Q (flat, from sq_forward) -> E in the plan's layout: the INTERIOR of
-    the reference's padded E (nw.py:138-175, 339), i.e. dVt/dtheta."""
+    the reference's padded E (nw.py:138-175, 339), i.e. dVt/dtheta.  out: a caller-owned buffer for E."""
     _check_in("Et", Et, (plan.B,))
     Et = Et.detach()
     with torch.cuda.device(Q.device):
-        E = _sq_out_like(plan, Q)
+        if out is not None:
+            E = _sq_take_out("E", out, plan.packed_floats, Q.device)
+            if plan.packed or plan.ragged:
+                E[:plan.packed_floats].zero_()         # padding floats / cells outside a pair's corner read as zero
+        else:
+            E = _sq_out_like(plan, Q)
         if CLUSTER_BWD and _use_cluster(plan, flags):
             rc = _lib.lib().b200dp_cl_bwd(_ptr(Et), Et.stride(0) if plan.B > 0 else 0, _ptr(Q), _ptr(E), plan.B, plan.N,
                                           plan.M, MODES[mode], 0, _stream(Q))

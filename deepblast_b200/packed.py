@@ -50,8 +50,14 @@ class PackedHostDecoder:
             self.s_in = torch.cuda.Stream(device=self.device)
             self.s_cmp = torch.cuda.Stream(device=self.device)
             self.s_out = torch.cuda.Stream(device=self.device)
-            self.slots = [(torch.empty(cap, dtype=torch.float32, device=self.device),
-                           torch.empty(cap, dtype=torch.float32, device=self.device)) for _ in range(3)]
+            # per slot: theta, A, E (packed floats of the largest chunk), Q (its strip-major floats), Vt -- nothing
+            # is allocated inside decode(): an allocation there can fall through to cudaMalloc (a device-wide
+            # synchronisation in the middle of the pipeline) whenever the caching allocator has no block ready
+            qcap = max(int(sub.q_floats) for _, _, _, _, sub in self.chunks)
+            bcap = max(b1 - b0 for b0, b1, _, _, _ in self.chunks)
+            mk = lambda n: torch.empty(n, dtype=torch.float32, device=self.device)      # noqa: E731
+            self.slots = [(mk(cap), mk(cap), mk(cap), mk(qcap), mk(bcap)) for _ in range(3)]
+            self.out_done = [torch.cuda.Event() for _ in range(3)]
             self.cmp_done = [torch.cuda.Event() for _ in range(3)]
             self.ones = torch.ones(self.B, dtype=torch.float32, device=self.device)
         self.Vt_h = torch.empty(self.B, dtype=torch.float32, pin_memory=True)
@@ -66,7 +72,7 @@ class PackedHostDecoder:
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_stream(cur)
         for c, (b0, b1, o0, o1, sub) in enumerate(self.chunks):
-            th_d, a_d = self.slots[c % 3]
+            th_d, a_d, e_d, q_d, vt_d = self.slots[c % 3]
             n = o1 - o0
             with torch.cuda.stream(self.s_in):
                 self.s_in.wait_event(self.cmp_done[c % 3])            # the slot's previous sweeps are done
@@ -76,17 +82,15 @@ class PackedHostDecoder:
                 up.record(self.s_in)
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(up)
-                Vt, Q = ops.sq_forward(sub, th_d[:n], a_d[:n], self.mode)
-                E = ops.sq_backward(sub, self.ones[b0:b1], Q, self.mode)
+                self.s_cmp.wait_event(self.out_done[c % 3])            # the slot's previous results have left
+                Vt, Q = ops.sq_forward(sub, th_d[:n], a_d[:n], self.mode, out=(vt_d, q_d))
+                E = ops.sq_backward(sub, self.ones[b0:b1], Q, self.mode, out=e_d)
                 self.cmp_done[c % 3].record(self.s_cmp)
-                done = torch.cuda.Event()
-                done.record(self.s_cmp)
             with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(done)
-                E_h[o0:o1].copy_(E, non_blocking=True)
-                Vt_h[b0:b1].copy_(Vt, non_blocking=True)
-                E.record_stream(self.s_out)
-                Vt.record_stream(self.s_out)
+                self.s_out.wait_event(self.cmp_done[c % 3])
+                E_h[o0:o1].copy_(E[:n], non_blocking=True)
+                Vt_h[b0:b1].copy_(Vt[:b1 - b0], non_blocking=True)
+                self.out_done[c % 3].record(self.s_out)
         cur.wait_stream(self.s_out)
         return Vt_h, E_h
 
