@@ -340,6 +340,16 @@ def _sq_take_out(name, t, numel, device):
     return t
 
 
+def score_plan(theta, xlen=None, ylen=None):
+    """The plan for a forward whose Q nobody will read, or None when the strip-queue kernels do not take
+    the shape (M % 4 != 0 in the dense layout)."""
+    from . import plan as _plan
+    if SQ_MODE == "never" or not theta.is_cuda or theta.dim() != 3 or theta.shape[0] == 0 or theta.shape[2] % 4 != 0:
+        return None
+    B, N, M = theta.shape
+    return _plan.get_plan(B, N, M, xlen, ylen, False, theta.device)
+
+
 def sq_forward(plan, theta, A, mode="nw", need_q=True, flags=0, out=None):
     """theta, A in the plan's layout (dense [B,N,M] or a flat packed buffer) -> (Vt [B], Q flat
     strip-major buffer, or None with need_q=False: score only).  nw.py:65-117 per pair.

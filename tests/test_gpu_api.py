@@ -396,3 +396,22 @@ def test_host_aligner_paths_match_device_decode_and_oracle_walk(mode, ragged):
             e2 = E_o[0, 1:-1, 1:-1]
             assert got == O.traceback(e2, "cuda") or len(got) == len(want)
         assert strings[b] == ''.join({0: '1', 1: ':', 2: '2'}[s] for _, _, s in got)
+
+
+@pytest.mark.parametrize("mode", ["nw", "sw"])
+def test_large_batch_score_without_grad_skips_q(mode):
+    """NeuralAligner.score (alignment.py:127-137) calls ddp(theta, A) under no_grad: also a large equal-size
+    batch then runs the score-only forward (no Q written) and returns the same Vt as the differentiable call."""
+    from deepblast_b200 import ops
+    B, N, M = 600, 64, 96
+    g = torch.Generator(device=dev()).manual_seed(8)
+    theta = torch.rand(B, N, M, generator=g, device=dev())
+    A = -torch.rand(B, N, M, generator=g, device=dev())
+    dec = decoders()[mode]('softmax')
+    assert ops.route_plan(theta) is None                    # the chained kernels' territory
+    with torch.no_grad():
+        v0 = dec(theta, A)
+    v1 = dec(theta.clone().requires_grad_(), A.clone().requires_grad_())
+    np.testing.assert_allclose(v0.cpu().numpy(), v1.detach().cpu().numpy(), rtol=2e-6)
+    Vt_o, _ = O.forward_pass(theta[:3].cpu().numpy(), A[:3].cpu().numpy(), mode)
+    np.testing.assert_allclose(v0[:3].cpu().numpy(), Vt_o, rtol=1e-6)
