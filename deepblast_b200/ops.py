@@ -248,11 +248,18 @@ def adjoint_pair_fast(Q, E, Ztheta, ZA=None, N=None, flags=0, interior=False, Ei
         if ZA is not None:
             _check_in("ZA", ZA, (B, N, M))
             za = ZA.detach().contiguous()
-        QdE = q_empty(B, N, M, Q.device)
-        Vtd = torch.empty(B, dtype=torch.float32, device=Q.device)
-        rc = _lib.lib().b200dp_adj_fwd3(_ptr(Q), _ptr(zt), _ptr(za), _ptr(e), _ptr(Vtd), _ptr(QdE),
-                                        B, N, M, flags, _stream(Q))
-        _lib.check(rc, "b200dp_adj_fwd3")
+        if SQ_MODE != "never" and M % 4 == 0 and not flags:
+            # the adjoint FORWARD sweep on the strip-queue kernel (more warps per SM than one per pair; measured
+            # on B200: 1024 x 256^2 0.280 against 0.306 ms, 1024 x 512^2 1.03 against 1.12; the same values bit
+            # for bit, the same Qd * E layout), the adjoint BACKWARD stays on the chained kernel (0.224 / 0.230)
+            from . import plan as _plan
+            Vtd, QdE = sq_adjoint_forward(_plan.get_plan(B, N, M, None, None, False, Q.device), Q, zt, za, e)
+        else:
+            QdE = q_empty(B, N, M, Q.device)
+            Vtd = torch.empty(B, dtype=torch.float32, device=Q.device)
+            rc = _lib.lib().b200dp_adj_fwd3(_ptr(Q), _ptr(zt), _ptr(za), _ptr(e), _ptr(Vtd), _ptr(QdE),
+                                            B, N, M, flags, _stream(Q))
+            _lib.check(rc, "b200dp_adj_fwd3")
         # interior_out: Ed[:, 1:-1, 1:-1] as a contiguous [B, N, M] tensor, no padded Ed at all
         Ed = None if interior_out else torch.empty((B, N2, M2), dtype=torch.float32, device=Q.device)
         Edi = torch.empty((B, N, M), dtype=torch.float32, device=Q.device) if interior_out else None
