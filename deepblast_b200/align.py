@@ -80,7 +80,7 @@ class HostAligner:
         if M % 4 != 0:
             raise RuntimeError("HostAligner needs M % 4 == 0 (16-byte rows)")
         if chunk_pairs is None:
-            chunk_pairs = max(1, min(B, max(8, (4 << 20) // max(1, N * M)), (B + 11) // 12 if B >= 24 else B))
+            chunk_pairs = max(1, min(B, max(8, (6 << 20) // max(1, N * M)), (B + 9) // 10 if B >= 20 else B))
         self.cap = _lib.lib().b200dp_align_host_path_cap(N, M)
         self.chunk_pairs = int(chunk_pairs)
         self.native = xlen is None and ylen is None

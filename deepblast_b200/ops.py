@@ -551,7 +551,7 @@ def decode_host_async(theta_h, A_h, mode="nw", Et_h=None, chunk_pairs=None, out=
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     if chunk_pairs is None:
         # enough chunks to hide the first upload and the last download, each still a few MB
-        chunk_pairs = max(1, min(B, max(8, (4 << 20) // max(1, N * M)), (B + 11) // 12 if B >= 24 else B))
+        chunk_pairs = max(1, min(B, max(8, (6 << 20) // max(1, N * M)), (B + 9) // 10 if B >= 20 else B))
     with torch.cuda.device(dev):
         need = _lib.lib().b200dp_decode_host_workspace(N, M, chunk_pairs)
         key = (dev.index, N, M, chunk_pairs)
