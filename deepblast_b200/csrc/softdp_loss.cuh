@@ -54,15 +54,27 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 // (zero-filled by b200dp_mxent_fwd), a small kernel then forms l_b / B.
 constexpr int kLossRows = 32;
 
+// Ytrue is an alignment indicator (0 or 1) in every caller: one of the two terms then has the factor 0 and
+// its logarithm / quotient need not be formed (both are finite: q is clamped into [eps, 1 - 2^-24]), which
+// takes the kernels off the issue limit -- logf and the IEEE division are ~20 and ~10 instructions.  The
+// result is the same bit for bit (x * 1 + finite * 0 = x); fractional labels take the general expression.
 __device__ __forceinline__ float mxent_term(float y, float q0, float g, float& c) {
     const bool on = g != 0.f;
     const float q = fminf(fmaxf(q0, kLossEps), kLossMax);
     c += on ? 1.f : 0.f;
+    if (y == 1.f || y == 0.f) {
+        const float l = logf(y == 1.f ? q : 1.f - q);
+        return on ? l : 0.f;
+    }
     return on ? y * logf(q) + (1.f - y) * logf(1.f - q) : 0.f;
 }
 __device__ __forceinline__ float mxent_grad(float y, float q0, float g, float scale) {
     // clamp passes the gradient only inside [eps, max] (torch.clamp backward)
     const bool on = g != 0.f && q0 >= kLossEps && q0 <= kLossMax;
+    if (y == 1.f || y == 0.f) {
+        const float d = (y == 1.f) ? 1.f / q0 : -(1.f / (1.f - q0));
+        return on ? scale * d : 0.f;
+    }
     return on ? scale * (y / q0 - (1.f - y) / (1.f - q0)) : 0.f;
 }
 
