@@ -192,8 +192,11 @@ int launch_fwd3_t(const CUtensorMap& tmT, const CUtensorMap& tmA, const CUtensor
         rc = set_smem(kern, smem, "b200dp_fwd");
         if (!rc) kern<<<grid, 32, smem, st>>>(tmT, tmA, pfT, pfA, p);
     };
-    if (sw) run(softdp_fwd3_kernel<true, NCH, RING>);
-    else run(softdp_fwd3_kernel<false, NCH, RING>);
+#ifndef B200DP_FWD3_DBG
+#define B200DP_FWD3_DBG 0        // diagnostic builds (scripts/gpu_x16.sh): fwd2_step's DBG bits; results are wrong
+#endif
+    if (sw) run(softdp_fwd3_kernel<true, NCH, RING, B200DP_FWD3_DBG>);
+    else run(softdp_fwd3_kernel<false, NCH, RING, B200DP_FWD3_DBG>);
     return rc;
 }
 

@@ -47,10 +47,22 @@ __host__ __device__ inline size_t fwd2_smem_bytes(int W, int M) {
 // rule.  hup = h of the row above at this column, v = the lane's own vertical difference
 // at the previous column (in), this column (out); returns h of this cell.
 // DBG: bit 0 = drop the Q stores but keep the arithmetic, bit 1 = no theta/A staging (both
-// diagnostic builds only); bit 2 = score-only forward (no Q at all).
+// diagnostic builds only); bit 2 = score-only forward (no Q at all); bit 3 = memory skeleton (diagnostic
+// builds only: the loads, the shuffle and the stores of a step with one FMA in place of the cell arithmetic).
 template <bool EDGE, bool SWM, int DBG = 0>
 __device__ __forceinline__ float fwd2_step(float th, float a, float hup, float& v, float* __restrict__ qp,
                                            bool store, bool comp) {
+    if (DBG & 8) {
+        const float hn = fmaf(v, 0.5f, th), vn = fmaf(hup, 0.5f, a);
+        if (DBG & 1) {
+            if (hn + vn == 12345.f) qp[0] = hn;
+        } else if (!EDGE || store) {
+            qp[0] = hn;
+            qp[kQY] = vn;
+        }
+        v = vn;
+        return hn;
+    }
     const float dx = fmaf(a, kLog2e, hup);           // u_x - u_m   (nw.py:56-58), log2 units
     const float dy = fmaf(a, kLog2e, v);             // u_y - u_m
     // softmax / logsumexp over (dx, 0, dy), nw.py:10-27, relative to the maximum (one
