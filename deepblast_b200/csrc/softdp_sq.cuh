@@ -39,6 +39,10 @@
 
 namespace b200dp {
 
+#ifndef B200DP_SQ_REARM
+#define B200DP_SQ_REARM 3
+#endif
+constexpr int kSqRearmStep = B200DP_SQ_REARM;   // step of a backward block at which the block's own Q slot is re-armed (its Q is in registers by then)
 constexpr int kSqPfStep = 11;    // step of a 16-step block at which the next block's boundary entries are fetched
 constexpr int kSqFirst = 1;      // StripRec.flags: strip 0 of its pair (holds lattice row 1)
 constexpr int kSqLast = 2;       //                 last strip of its pair (holds lattice row n)
@@ -587,13 +591,17 @@ __global__ void __launch_bounds__(32) softdp_sq_bwd_kernel(const SqParams p) {
                 nxt = sq_load_rec(p.tab, nxt_tk, p.nstrips);
                 nxt_ready = true;
             }
-            while (issued <= b + RING - 1) {
-                if (issued < NBk) issue(cur, issued, islot);
-                else if (nxt_ready && nxt.rows > 0 && issued - NBk < ((nxt.m + 31 + 15) >> 4)) issue(nxt, issued - NBk, islot);
-                else break;
-                issued++;
-                islot = (islot + 1 == RING) ? 0u : islot + 1;
-            }
+            // tiles up to `limit` go out (this strip's, then the next strip's first ones)
+            auto pump = [&](int limit) {
+                while (issued <= limit) {
+                    if (issued < NBk) issue(cur, issued, islot);
+                    else if (nxt_ready && nxt.rows > 0 && issued - NBk < ((nxt.m + 31 + 15) >> 4)) issue(nxt, issued - NBk, islot);
+                    else break;
+                    issued++;
+                    islot = (islot + 1 == RING) ? 0u : islot + 1;
+                }
+            };
+            pump(b + RING - 1);
             mbar_wait(&bars[wslot], (phases >> wslot) & 1u);
             phases ^= 1u << wslot;
             const float* qt = qring + wslot * kSlotElems + t;
@@ -700,6 +708,13 @@ __global__ void __launch_bounds__(32) softdp_sq_bwd_kernel(const SqParams p) {
                     if (t == 0 && feeds_up && (!EDGE || (row_ok && (unsigned)(m + 30 - s0 - ss) < (unsigned)m)))
                         sq_publish(bw - ss, sq_pack(epoch, zout), p.dbg);
                     if (ss == kSqPfStep && pf_next) pfv = ld_relaxed_gpu_u64(bin + cn);
+                    if (ss == kSqRearmStep) {
+                        // the block's Q is in registers (shared-memory loads of a warp return in order: when the
+                        // gate is back, so are they), so its slot can take the tile RING blocks ahead now instead
+                        // of at the top of the next block: RING tiles in flight instead of RING - 1
+                        const float gate = *reinterpret_cast<const volatile float*>(zero_row);
+                        if (gate == 0.f) pump(b + RING);
+                    }
                 }
             };
             if (steady) block(std::false_type{});
