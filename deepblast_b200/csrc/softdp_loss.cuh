@@ -138,8 +138,18 @@ __global__ void softdp_mxent_fin_kernel(LossParams p) {
         p.pair_loss[b] = -(p.pair_loss[b] / p.pair_count[b]) / (float)p.B;   // mean of an empty selection is NaN, as in torch
 }
 
+// The backward is a pure streaming pass (16 B/cell) with an IEEE division per cell: at 96 registers (two CTAs
+// per SM) it ran at 0.210 ms for C2; four CTAs per SM with two rows (six 16-byte loads) in flight per lane:
+// 0.168 ms (measured on B200, scripts/gpu_loss_perf.py).
+#ifndef B200DP_LOSS_MINB
+#define B200DP_LOSS_MINB 4
+#endif
+#ifndef B200DP_LOSS_BROWS
+#define B200DP_LOSS_BROWS 2
+#endif
+constexpr int kLossBwdRows = B200DP_LOSS_BROWS;     // rows of a warp's four loaded together (1, 2 or 4)
 template <bool VEC>
-__global__ void __launch_bounds__(256) softdp_mxent_bwd_kernel(LossParams p) {
+__global__ void __launch_bounds__(256, B200DP_LOSS_MINB) softdp_mxent_bwd_kernel(LossParams p) {
     const int b = blockIdx.y;
     const int n = p.xlen ? min(max(p.xlen[b], 0), p.N) : p.N;
     const int m = p.ylen ? min(max(p.ylen[b], 0), p.M) : p.M;
@@ -152,27 +162,30 @@ __global__ void __launch_bounds__(256) softdp_mxent_bwd_kernel(LossParams p) {
     const int r0 = blockIdx.x * kLossRows + 4 * w;
     if (VEC) {
         const int M4 = p.M >> 2;
-        for (int c4 = lane; c4 < M4; c4 += 32) {
-            float4 y4[4], q4[4], g4[4];
+        // kLossBwdRows rows at a time: 3 * kLossBwdRows independent 16-byte loads in flight per lane
+        for (int rr = 0; rr < 4; rr += kLossBwdRows) {
+            for (int c4 = lane; c4 < M4; c4 += 32) {
+                float4 y4[kLossBwdRows], q4[kLossBwdRows], g4[kLossBwdRows];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int i = min(r0 + r, p.N - 1);
-                y4[r] = reinterpret_cast<const float4*>(yt + (long long)i * p.M)[c4];
-                q4[r] = reinterpret_cast<const float4*>(yp + (long long)i * p.pi)[c4];
-                g4[r] = gm ? reinterpret_cast<const float4*>(gm + (long long)i * p.M)[c4] : make_float4(1.f, 1.f, 1.f, 1.f);
-            }
+                for (int r = 0; r < kLossBwdRows; ++r) {
+                    const int i = min(r0 + rr + r, p.N - 1);
+                    y4[r] = reinterpret_cast<const float4*>(yt + (long long)i * p.M)[c4];
+                    q4[r] = reinterpret_cast<const float4*>(yp + (long long)i * p.pi)[c4];
+                    g4[r] = gm ? reinterpret_cast<const float4*>(gm + (long long)i * p.M)[c4] : make_float4(1.f, 1.f, 1.f, 1.f);
+                }
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int i = r0 + r;
-                if (i >= p.N) break;
-                const int j = 4 * c4;
-                const float ki = i < n ? 1.f : 0.f;                      // zeros outside the pair's lattice
-                float4 o;
-                o.x = mxent_grad(y4[r].x, q4[r].x, g4[r].x * (j < m ? ki : 0.f), scale);
-                o.y = mxent_grad(y4[r].y, q4[r].y, g4[r].y * (j + 1 < m ? ki : 0.f), scale);
-                o.z = mxent_grad(y4[r].z, q4[r].z, g4[r].z * (j + 2 < m ? ki : 0.f), scale);
-                o.w = mxent_grad(y4[r].w, q4[r].w, g4[r].w * (j + 3 < m ? ki : 0.f), scale);
-                reinterpret_cast<float4*>(gr + (long long)i * p.M)[c4] = o;
+                for (int r = 0; r < kLossBwdRows; ++r) {
+                    const int i = r0 + rr + r;
+                    if (i >= p.N) break;
+                    const int j = 4 * c4;
+                    const float ki = i < n ? 1.f : 0.f;                      // zeros outside the pair's lattice
+                    float4 o;
+                    o.x = mxent_grad(y4[r].x, q4[r].x, g4[r].x * (j < m ? ki : 0.f), scale);
+                    o.y = mxent_grad(y4[r].y, q4[r].y, g4[r].y * (j + 1 < m ? ki : 0.f), scale);
+                    o.z = mxent_grad(y4[r].z, q4[r].z, g4[r].z * (j + 2 < m ? ki : 0.f), scale);
+                    o.w = mxent_grad(y4[r].w, q4[r].w, g4[r].w * (j + 3 < m ? ki : 0.f), scale);
+                    reinterpret_cast<float4*>(gr + (long long)i * p.M)[c4] = o;
+                }
             }
         }
     } else {
