@@ -58,24 +58,36 @@ constexpr int kLossRows = 32;
 // its logarithm / quotient need not be formed (both are finite: q is clamped into [eps, 1 - 2^-24]), which
 // takes the kernels off the issue limit -- logf and the IEEE division are ~20 and ~10 instructions.  The
 // result is the same bit for bit (x * 1 + finite * 0 = x); fractional labels take the general expression.
+// (BIN is decided once per 16 cells for the whole warp -- a vote -- so the vector loops carry no per-cell branch)
+template <bool BIN>
 __device__ __forceinline__ float mxent_term(float y, float q0, float g, float& c) {
     const bool on = g != 0.f;
     const float q = fminf(fmaxf(q0, kLossEps), kLossMax);
     c += on ? 1.f : 0.f;
-    if (y == 1.f || y == 0.f) {
+    if (BIN) {
         const float l = logf(y == 1.f ? q : 1.f - q);
         return on ? l : 0.f;
     }
     return on ? y * logf(q) + (1.f - y) * logf(1.f - q) : 0.f;
 }
+__device__ __forceinline__ float mxent_term(float y, float q0, float g, float& c) {
+    return (y == 1.f || y == 0.f) ? mxent_term<true>(y, q0, g, c) : mxent_term<false>(y, q0, g, c);
+}
+template <bool BIN>
 __device__ __forceinline__ float mxent_grad(float y, float q0, float g, float scale) {
     // clamp passes the gradient only inside [eps, max] (torch.clamp backward)
     const bool on = g != 0.f && q0 >= kLossEps && q0 <= kLossMax;
-    if (y == 1.f || y == 0.f) {
+    if (BIN) {
         const float d = (y == 1.f) ? 1.f / q0 : -(1.f / (1.f - q0));
         return on ? scale * d : 0.f;
     }
     return on ? scale * (y / q0 - (1.f - y) / (1.f - q0)) : 0.f;
+}
+__device__ __forceinline__ float mxent_grad(float y, float q0, float g, float scale) {
+    return (y == 1.f || y == 0.f) ? mxent_grad<true>(y, q0, g, scale) : mxent_grad<false>(y, q0, g, scale);
+}
+__device__ __forceinline__ bool is_binary(const float4& y) {
+    return (y.x == 1.f || y.x == 0.f) && (y.y == 1.f || y.y == 0.f) && (y.z == 1.f || y.z == 0.f) && (y.w == 1.f || y.w == 0.f);
 }
 
 template <bool VEC>
@@ -103,12 +115,18 @@ __global__ void __launch_bounds__(256) softdp_mxent_fwd_kernel(LossParams p) {
                 q4[r] = reinterpret_cast<const float4*>(yp + (long long)i * p.pi)[c4];
                 g4[r] = gm ? reinterpret_cast<const float4*>(gm + (long long)i * p.M)[c4] : make_float4(1.f, 1.f, 1.f, 1.f);
             }
+            auto add = [&](auto bin_tag) {
+                constexpr bool BIN = decltype(bin_tag)::value;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float k = (r0 + r < n) ? 1.f : 0.f;
-                s += mxent_term(y4[r].x, q4[r].x, g4[r].x * k, c) + mxent_term(y4[r].y, q4[r].y, g4[r].y * k, c) +
-                     mxent_term(y4[r].z, q4[r].z, g4[r].z * k, c) + mxent_term(y4[r].w, q4[r].w, g4[r].w * k, c);
-            }
+                for (int r = 0; r < 4; ++r) {
+                    const float k = (r0 + r < n) ? 1.f : 0.f;
+                    s += mxent_term<BIN>(y4[r].x, q4[r].x, g4[r].x * k, c) + mxent_term<BIN>(y4[r].y, q4[r].y, g4[r].y * k, c) +
+                         mxent_term<BIN>(y4[r].z, q4[r].z, g4[r].z * k, c) + mxent_term<BIN>(y4[r].w, q4[r].w, g4[r].w * k, c);
+                }
+            };
+            const bool bin = is_binary(y4[0]) && is_binary(y4[1]) && is_binary(y4[2]) && is_binary(y4[3]);
+            if (__all_sync(__activemask(), bin)) add(std::true_type{});
+            else add(std::false_type{});
         }
         // the m % 4 tail columns
         for (int j = 4 * m4 + lane; j < m; j += 32)
@@ -173,19 +191,27 @@ __global__ void __launch_bounds__(256, B200DP_LOSS_MINB) softdp_mxent_bwd_kernel
                     q4[r] = reinterpret_cast<const float4*>(yp + (long long)i * p.pi)[c4];
                     g4[r] = gm ? reinterpret_cast<const float4*>(gm + (long long)i * p.M)[c4] : make_float4(1.f, 1.f, 1.f, 1.f);
                 }
+                auto put = [&](auto bin_tag) {
+                    constexpr bool BIN = decltype(bin_tag)::value;
 #pragma unroll
-                for (int r = 0; r < kLossBwdRows; ++r) {
-                    const int i = r0 + rr + r;
-                    if (i >= p.N) break;
-                    const int j = 4 * c4;
-                    const float ki = i < n ? 1.f : 0.f;                      // zeros outside the pair's lattice
-                    float4 o;
-                    o.x = mxent_grad(y4[r].x, q4[r].x, g4[r].x * (j < m ? ki : 0.f), scale);
-                    o.y = mxent_grad(y4[r].y, q4[r].y, g4[r].y * (j + 1 < m ? ki : 0.f), scale);
-                    o.z = mxent_grad(y4[r].z, q4[r].z, g4[r].z * (j + 2 < m ? ki : 0.f), scale);
-                    o.w = mxent_grad(y4[r].w, q4[r].w, g4[r].w * (j + 3 < m ? ki : 0.f), scale);
-                    reinterpret_cast<float4*>(gr + (long long)i * p.M)[c4] = o;
-                }
+                    for (int r = 0; r < kLossBwdRows; ++r) {
+                        const int i = r0 + rr + r;
+                        if (i >= p.N) break;
+                        const int j = 4 * c4;
+                        const float ki = i < n ? 1.f : 0.f;                      // zeros outside the pair's lattice
+                        float4 o;
+                        o.x = mxent_grad<BIN>(y4[r].x, q4[r].x, g4[r].x * (j < m ? ki : 0.f), scale);
+                        o.y = mxent_grad<BIN>(y4[r].y, q4[r].y, g4[r].y * (j + 1 < m ? ki : 0.f), scale);
+                        o.z = mxent_grad<BIN>(y4[r].z, q4[r].z, g4[r].z * (j + 2 < m ? ki : 0.f), scale);
+                        o.w = mxent_grad<BIN>(y4[r].w, q4[r].w, g4[r].w * (j + 3 < m ? ki : 0.f), scale);
+                        reinterpret_cast<float4*>(gr + (long long)i * p.M)[c4] = o;
+                    }
+                };
+                bool bin = true;
+#pragma unroll
+                for (int r = 0; r < kLossBwdRows; ++r) bin = bin && is_binary(y4[r]);
+                if (__all_sync(__activemask(), bin)) put(std::true_type{});
+                else put(std::false_type{});
             }
         }
     } else {
