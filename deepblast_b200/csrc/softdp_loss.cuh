@@ -45,11 +45,12 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 // Grid (row slabs, pairs): a CTA takes kLossRows rows of one pair, warp w the four rows
-// 4w .. 4w+3 of the slab.  All loads of a step -- G, Ytrue and Ypred of four rows, 16 bytes per
+// 4w .. 4w+3 of the slab.  All loads of a step -- G, Ytrue and Ypred of two rows, 16 bytes per
 // lane where the row pitches allow (M and the Ypred pitch multiples of 4, 16-byte aligned bases)
 // -- are issued before anything is used, unconditionally (the mask is applied to the values,
-// not to the loads), so a lane has 12 independent 16-byte loads in flight: the kernels are pure
-// streaming passes (12 B/cell forward, 16 B/cell backward) and need the memory-level
+// not to the loads), so a lane has 6 independent 16-byte loads in flight at four CTAs per SM
+// (measured on B200: better than 12 loads per lane at two or three CTAs per SM): the kernels are
+// pure streaming passes (12 B/cell forward, 16 B/cell backward) and need the memory-level
 // parallelism.  Slabs add their partial (sum, count) to the pair's totals with atomics
 // (zero-filled by b200dp_mxent_fwd), a small kernel then forms l_b / B.
 constexpr int kLossRows = 32;
@@ -90,8 +91,15 @@ __device__ __forceinline__ bool is_binary(const float4& y) {
     return (y.x == 1.f || y.x == 0.f) && (y.y == 1.f || y.y == 0.f) && (y.z == 1.f || y.z == 0.f) && (y.w == 1.f || y.w == 0.f);
 }
 
+#ifndef B200DP_LOSS_FMINB
+#define B200DP_LOSS_FMINB 4
+#endif
+#ifndef B200DP_LOSS_FROWS
+#define B200DP_LOSS_FROWS 2
+#endif
+constexpr int kLossFwdRows = B200DP_LOSS_FROWS;
 template <bool VEC>
-__global__ void __launch_bounds__(256) softdp_mxent_fwd_kernel(LossParams p) {
+__global__ void __launch_bounds__(256, B200DP_LOSS_FMINB) softdp_mxent_fwd_kernel(LossParams p) {
     __shared__ float red[8];
     const int b = blockIdx.y;
     const int n = p.xlen ? min(max(p.xlen[b], 0), p.N) : p.N;
@@ -107,26 +115,32 @@ __global__ void __launch_bounds__(256) softdp_mxent_fwd_kernel(LossParams p) {
     if (VEC) {
         const int m4 = m >> 2;                           // whole float4 groups inside the pair's columns
         for (int c4 = lane; c4 < m4; c4 += 32) {
-            float4 y4[4], q4[4], g4[4];
+            // kLossFwdRows rows at a time (the order of the additions does not depend on it)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int i = min(r0 + r, n - 1);       // rows past the pair: reload the last row, weight 0
-                y4[r] = reinterpret_cast<const float4*>(yt + (long long)i * p.M)[c4];
-                q4[r] = reinterpret_cast<const float4*>(yp + (long long)i * p.pi)[c4];
-                g4[r] = gm ? reinterpret_cast<const float4*>(gm + (long long)i * p.M)[c4] : make_float4(1.f, 1.f, 1.f, 1.f);
-            }
-            auto add = [&](auto bin_tag) {
-                constexpr bool BIN = decltype(bin_tag)::value;
+            for (int rr = 0; rr < 4; rr += kLossFwdRows) {
+                float4 y4[kLossFwdRows], q4[kLossFwdRows], g4[kLossFwdRows];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float k = (r0 + r < n) ? 1.f : 0.f;
-                    s += mxent_term<BIN>(y4[r].x, q4[r].x, g4[r].x * k, c) + mxent_term<BIN>(y4[r].y, q4[r].y, g4[r].y * k, c) +
-                         mxent_term<BIN>(y4[r].z, q4[r].z, g4[r].z * k, c) + mxent_term<BIN>(y4[r].w, q4[r].w, g4[r].w * k, c);
+                for (int r = 0; r < kLossFwdRows; ++r) {
+                    const int i = min(r0 + rr + r, n - 1);       // rows past the pair: reload the last row, weight 0
+                    y4[r] = reinterpret_cast<const float4*>(yt + (long long)i * p.M)[c4];
+                    q4[r] = reinterpret_cast<const float4*>(yp + (long long)i * p.pi)[c4];
+                    g4[r] = gm ? reinterpret_cast<const float4*>(gm + (long long)i * p.M)[c4] : make_float4(1.f, 1.f, 1.f, 1.f);
                 }
-            };
-            const bool bin = is_binary(y4[0]) && is_binary(y4[1]) && is_binary(y4[2]) && is_binary(y4[3]);
-            if (__all_sync(__activemask(), bin)) add(std::true_type{});
-            else add(std::false_type{});
+                auto add = [&](auto bin_tag) {
+                    constexpr bool BIN = decltype(bin_tag)::value;
+#pragma unroll
+                    for (int r = 0; r < kLossFwdRows; ++r) {
+                        const float k = (r0 + rr + r < n) ? 1.f : 0.f;
+                        s += mxent_term<BIN>(y4[r].x, q4[r].x, g4[r].x * k, c) + mxent_term<BIN>(y4[r].y, q4[r].y, g4[r].y * k, c) +
+                             mxent_term<BIN>(y4[r].z, q4[r].z, g4[r].z * k, c) + mxent_term<BIN>(y4[r].w, q4[r].w, g4[r].w * k, c);
+                    }
+                };
+                bool bin = true;
+#pragma unroll
+                for (int r = 0; r < kLossFwdRows; ++r) bin = bin && is_binary(y4[r]);
+                if (__all_sync(__activemask(), bin)) add(std::true_type{});
+                else add(std::false_type{});
+            }
         }
         // the m % 4 tail columns
         for (int j = 4 * m4 + lane; j < m; j += 32)

@@ -9,6 +9,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from deepblast_b200 import _lib  # noqa: E402
+if os.environ.get("LIB"):            # alternative build of the library
+    _lib.LIB_PATH = os.path.abspath(os.environ["LIB"])
 from deepblast_b200.nw_cuda import NeedlemanWunschDecoder  # noqa: E402
 from deepblast_b200.losses import MatrixCrossEntropy  # noqa: E402
 
