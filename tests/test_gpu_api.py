@@ -281,6 +281,39 @@ def test_matrix_cross_entropy_on_decode_output():
     np.testing.assert_allclose(g1.cpu().numpy(), g2.cpu().numpy(), rtol=0, atol=2e-4 * scale)
 
 
+@pytest.mark.parametrize("labels", ["binary", "fractional", "mixed"])
+def test_matrix_cross_entropy_label_paths(labels):
+    """The vector kernels pick the one-logarithm / one-quotient path by a warp vote over 16 cells (labels all
+    0 or 1) and the general expression otherwise: both, and batches where only some warps vote yes, against
+    the reference's formula (losses.py:9-48) stated with torch ops, value and gradient."""
+    from deepblast_b200.losses import MatrixCrossEntropy
+    B, N, M = 3, 70, 136
+    g = torch.Generator().manual_seed(5)
+    Ypred = (torch.rand(B, N, M, generator=g) * 0.98 + 0.01).to(dev()).requires_grad_()
+    Ytrue = (torch.rand(B, N, M, generator=g) < 0.1).float()
+    if labels == "fractional":
+        Ytrue = torch.rand(B, N, M, generator=g)
+    elif labels == "mixed":
+        Ytrue[1, 10:20, 32:64] = 0.25                      # a few 16-cell groups with fractional labels
+        Ytrue[2, 69, 135] = 0.5
+    Ytrue = Ytrue.to(dev())
+    G = (torch.rand(B, N, M, generator=g) < 0.9).float().to(dev())
+    xlen, ylen = [70, 41, 70], [136, 99, 136]
+    loss = MatrixCrossEntropy()(Ytrue, Ypred, xlen, ylen, G)
+    g1, = torch.autograd.grad(loss, Ypred)
+    Yp2 = Ypred.detach().clone().requires_grad_()
+    P = torch.clamp(Yp2, min=3e-8, max=1 - 3e-8)
+    ref = 0
+    for b in range(B):
+        sl = (b, slice(0, xlen[b]), slice(0, ylen[b]))
+        sel = G[sl] != 0
+        ref = ref - torch.mean((Ytrue[sl] * torch.log(P[sl]) + (1 - Ytrue[sl]) * torch.log(1 - P[sl]))[sel])
+    ref = ref / B
+    g2, = torch.autograd.grad(ref, Yp2)
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=2e-6)
+    np.testing.assert_allclose(g1.cpu().numpy(), g2.cpu().numpy(), rtol=1e-5, atol=1e-9)
+
+
 @pytest.mark.parametrize("mode", ["nw", "sw"])
 def test_replay_of_neuralaligner_call_pattern(mode):
     """What deepblast.alignment.NeuralAligner does with the decoder, call for call:
